@@ -1,0 +1,284 @@
+"""CPU oracle for the WeKws streaming keyword-spotting forward path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``wekws_b200/`` imports this module; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (its ``cpu_baseline`` leg
+and ``--impl reference`` arm) may.  It is the checker, never the product.
+
+It restates, op for op and in fp32 on the CPU, what the reference computes:
+
+* ``fbank``           -> torchaudio.compliance.kaldi.fbank as called from
+                         wekws/dataset/processor.py:173-203 and
+                         wekws/bin/stream_kws_ctc.py:354-360
+                         (torchaudio 2.11.0 kaldi.py:44-83 framing, :154-217
+                         window, :436-511 mel banks, :616-633 spectrum/mel/log)
+* ``global_cmvn``     -> wekws/model/cmvn.py:37-48
+* ``load_cmvn_json``  -> wekws/utils/cmvn.py:23-45
+* ``kws_forward``     -> wekws/model/kws_model.py:65-76 which composes
+                         subsampling.py:53-57, mdtc.py:95-121/181-198/242-276,
+                         tcn.py:35-61/75-84/101-114/139-166, torch.nn.GRU
+                         (kws_model.py:130-133), classifier.py:63-67 and the
+                         activation chosen at kws_model.py:196-210.
+
+The model is described by the ``model`` section of a reference yaml config (plus
+``input_dim``/``output_dim`` as wekws/bin/train.py:134-146 injects them) and a
+reference-format ``state_dict``.  The same ATen ops the reference dispatches to
+(conv1d, batch_norm with running stats, linear, gru) are used on purpose, so
+that timing this module on host cores is a fair stand-in for the reference's
+own CPU path on a machine where /root/reference does not exist.
+
+Parity pinning: ``tests/test_oracle_pinned.py`` checks every function here
+against golden vectors produced by the real reference (``oracle/make_golden.py``
+imports /root/reference and torchaudio and writes ``tests/golden/*.npz``), and,
+when /root/reference is present, against the live reference.
+"""
+from __future__ import annotations
+
+import json
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+EPS = float(torch.finfo(torch.float32).eps)  # kaldi.py:21
+BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by every BN in mdtc.py / tcn.py
+
+
+# --------------------------------------------------------------------------- Fbank
+def povey_window(n: int) -> Tensor:
+    """kaldi.py:98-100: hann(n, periodic=False) ** 0.85 in fp32."""
+    return torch.hann_window(n, periodic=False, dtype=torch.float32).pow(0.85)
+
+
+def hamming_window(n: int) -> Tensor:
+    """kaldi.py:96-97 / runtime/core/frontend/fbank.h:90-96."""
+    return torch.hamming_window(n, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32)
+
+
+def mel_scale(f: Tensor) -> Tensor:
+    return 1127.0 * (1.0 + f / 700.0).log()  # kaldi.py:330-331
+
+
+def mel_banks(num_bins: int, n_fft: int, sample_rate: float,
+              low_freq: float = 20.0, high_freq: float = 0.0) -> Tensor:
+    """kaldi.py:436-511 with vtln_warp == 1.0.  Returns (num_bins, n_fft//2 + 1);
+    the extra last column (Nyquist) is the zero pad of kaldi.py:627."""
+    num_fft_bins = n_fft // 2
+    nyquist = 0.5 * sample_rate
+    if high_freq <= 0.0:
+        high_freq += nyquist
+    fft_bin_width = sample_rate / n_fft
+    mel_low = 1127.0 * math.log(1.0 + low_freq / 700.0)
+    mel_high = 1127.0 * math.log(1.0 + high_freq / 700.0)
+    delta = (mel_high - mel_low) / (num_bins + 1)
+    b = torch.arange(num_bins).unsqueeze(1)
+    left = mel_low + b * delta
+    center = mel_low + (b + 1.0) * delta
+    right = mel_low + (b + 2.0) * delta
+    mel = mel_scale(fft_bin_width * torch.arange(num_fft_bins, dtype=torch.float32)).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    bins = torch.max(torch.zeros(1), torch.min(up, down))
+    return F.pad(bins, (0, 1), mode="constant", value=0.0)
+
+
+def num_frames(num_samples: int, frame_len: int = 400, frame_shift: int = 160) -> int:
+    """snip_edges framing, kaldi.py:66-70."""
+    if num_samples < frame_len:
+        return 0
+    return 1 + (num_samples - frame_len) // frame_shift
+
+
+def fbank(waveform: Tensor, num_mel_bins: int = 80, frame_length: float = 25.0,
+          frame_shift: float = 10.0, sample_frequency: float = 16000.0,
+          window_type: str = "povey", preemphasis: float = 0.97) -> Tensor:
+    """Kaldi log-mel filterbank of one waveform (N,) in int16-scale floats, with
+    the arguments the reference passes (dither=0, energy_floor=0, rest default).
+    Returns (m, num_mel_bins)."""
+    wav = waveform.to(torch.float32).reshape(-1)
+    win = int(sample_frequency * frame_length * 0.001)
+    shift = int(sample_frequency * frame_shift * 0.001)
+    n_fft = 1 if win == 0 else 2 ** (win - 1).bit_length()
+    m = num_frames(wav.numel(), win, shift)
+    if m == 0:
+        return torch.empty(0, num_mel_bins)
+    frames = wav.as_strided((m, win), (shift, 1))                         # kaldi.py:82-83
+    frames = frames - frames.mean(dim=1, keepdim=True)                    # :183-186
+    prev = F.pad(frames.unsqueeze(0), (1, 0), mode="replicate").squeeze(0)[:, :-1]
+    frames = frames - preemphasis * prev                                  # :193-198
+    w = povey_window(win) if window_type == "povey" else hamming_window(win)
+    frames = frames * w.unsqueeze(0)                                      # :201-204
+    frames = F.pad(frames, (0, n_fft - win))                              # :207-211
+    spec = torch.fft.rfft(frames).abs().pow(2.0)                          # :616-618
+    mel = mel_banks(num_mel_bins, n_fft, sample_frequency)                # :621-627
+    e = torch.mm(spec, mel.T)                                             # :630
+    return torch.max(e, torch.tensor(EPS)).log()                          # :633
+
+
+# ---------------------------------------------------------------------------- CMVN
+def load_cmvn_json(path: str) -> Tuple[Tensor, Tensor]:
+    """wekws/utils/cmvn.py:23-45, then the .float() of kws_model.py:104-108."""
+    with open(path) as f:
+        st = json.load(f)
+    n = st["frame_num"]
+    mean, istd = [], []
+    for s, v in zip(st["mean_stat"], st["var_stat"]):
+        mu = s / n
+        var = v / n - mu * mu
+        if var < 1.0e-20:
+            var = 1.0e-20
+        mean.append(mu)
+        istd.append(1.0 / math.sqrt(var))
+    return (torch.tensor(mean, dtype=torch.float64).float(),
+            torch.tensor(istd, dtype=torch.float64).float())
+
+
+def global_cmvn(x: Tensor, mean: Tensor, istd: Tensor, norm_var: bool = True) -> Tensor:
+    x = x - mean
+    if norm_var:
+        x = x * istd
+    return x
+
+
+# --------------------------------------------------------------------------- model
+def _bn(x: Tensor, sd: Dict[str, Tensor], p: str) -> Tensor:
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
+                        sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
+
+
+def _cat_cache(x: Tensor, cache: Optional[Tensor], pad: int) -> Tuple[Tensor, Tensor]:
+    """mdtc.py:108-113 == tcn.py:49-54."""
+    if cache is None:
+        y = F.pad(x, (pad, 0), value=0.0)
+    else:
+        y = torch.cat((cache, x), dim=2)
+    return y, y[:, :, -pad:]
+
+
+def _mdtc_block(x, cache, sd, p, k, d):
+    """mdtc.py:95-121 (TCNBlock) around mdtc.py:55-59 (DSDilatedConv1d)."""
+    C = x.size(1)
+    y, new_cache = _cat_cache(x, cache, d * (k - 1))
+    o = F.conv1d(y, sd[p + ".conv1.conv.weight"], sd[p + ".conv1.conv.bias"], dilation=d, groups=C)
+    o = _bn(o, sd, p + ".conv1.bn")
+    o = F.conv1d(o, sd[p + ".conv1.pointwise.weight"], sd[p + ".conv1.pointwise.bias"])
+    o = F.relu(_bn(o, sd, p + ".bn1"))
+    o = _bn(F.conv1d(o, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"]), sd, p + ".bn2")
+    return F.relu(o + x), new_cache
+
+
+def mdtc_layout(bb: dict):
+    """(prefix, dilation) of the 1 + num_stack*stack_size blocks in cache order
+    (mdtc.py:151-156, :236-237, :251-268)."""
+    blocks = [("backbone.preprocessor", 1)]
+    for s in range(bb["num_stack"]):
+        for l in range(bb["stack_size"]):
+            blocks.append((f"backbone.blocks.{s}.res_blocks.{l}", 2 ** l))
+    return blocks
+
+
+def _mdtc(x, cache, sd, bb):
+    k = bb["kernel_size"]
+    x = x.transpose(1, 2)
+    off, caches, outs = 0, [], []
+    for i, (p, d) in enumerate(mdtc_layout(bb)):
+        pad = d * (k - 1)
+        c_in = None if cache is None else cache[:, :, off:off + pad]
+        x, c = _mdtc_block(x, c_in, sd, p, k, d)
+        caches.append(c)
+        off += pad
+        if i > 0 and i % bb["stack_size"] == 0:
+            outs.append(x)                                   # mdtc.py:266
+    y = torch.zeros_like(outs[-1])
+    for o in outs:
+        y = y + o                                            # mdtc.py:270-273
+    return y.transpose(1, 2), torch.cat(caches, dim=2)
+
+
+def _tcn(x, cache, sd, bb):
+    k = bb.get("kernel_size", 8)
+    ds = bb.get("ds", False)
+    x = x.transpose(1, 2)
+    C = x.size(1)
+    off, caches = 0, []
+    for i in range(bb["num_layers"]):
+        d = 2 ** i
+        pad = (k - 1) * d
+        p = f"backbone.network.{i}.cnn"
+        c_in = None if cache is None else cache[:, :, off:off + pad]
+        y, c = _cat_cache(x, c_in, pad)
+        if ds:                                               # tcn.py:101-114
+            y = F.relu(_bn(F.conv1d(y, sd[p + ".0.weight"], sd[p + ".0.bias"], dilation=d, groups=C), sd, p + ".1"))
+            y = F.relu(_bn(F.conv1d(y, sd[p + ".3.weight"], sd[p + ".3.bias"]), sd, p + ".4"))
+        else:                                                # tcn.py:75-84
+            y = F.relu(_bn(F.conv1d(y, sd[p + ".0.weight"], sd[p + ".0.bias"], dilation=d), sd, p + ".1"))
+        x = y + x                                            # tcn.py:60
+        caches.append(c)
+        off += pad
+    return x.transpose(1, 2), torch.cat(caches, dim=2)
+
+
+_GRU_CACHE: dict = {}
+
+
+def _gru(x, cache, sd, bb, hdim):
+    """torch.nn.GRU(hdim, hdim, num_layers, batch_first=True), kws_model.py:130-133.
+    An empty cache raises in the reference (SURVEY: 'Expected hidden size ...');
+    start-of-stream therefore means an explicit zero h0 here."""
+    L = bb["num_layers"]
+    key = (id(sd), L, hdim)
+    g = _GRU_CACHE.get(key)
+    if g is None:
+        g = torch.nn.GRU(hdim, hdim, num_layers=L, batch_first=True)
+        with torch.no_grad():
+            for n, p in g.named_parameters():
+                p.copy_(sd["backbone." + n])
+        g.eval()
+        _GRU_CACHE.clear()
+        _GRU_CACHE[key] = g
+    if cache is None:
+        cache = x.new_zeros(L, x.size(0), hdim)
+    with torch.no_grad():
+        return g(x, cache)
+
+
+def backbone_padding(cfg: dict) -> int:
+    bb = cfg["backbone"]
+    if bb["type"] == "mdtc":
+        k = bb["kernel_size"]
+        return sum(d * (k - 1) for _, d in mdtc_layout(bb))
+    if bb["type"] == "tcn":
+        k = bb.get("kernel_size", 8)
+        return sum((k - 1) * 2 ** i for i in range(bb["num_layers"]))
+    return 0
+
+
+@torch.no_grad()
+def kws_forward(sd: Dict[str, Tensor], cfg: dict, feats: Tensor,
+                cache: Optional[Tensor] = None, softmax: bool = False) -> Tuple[Tensor, Tensor]:
+    """KWSModel.forward (kws_model.py:65-76); ``softmax=True`` is forward_softmax (:78-90).
+    ``cache`` None or of size(0)==0 means start of stream."""
+    if cache is not None and cache.numel() == 0:
+        cache = None
+    x = feats
+    if "global_cmvn.mean" in sd:
+        x = global_cmvn(x, sd["global_cmvn.mean"], sd["global_cmvn.istd"],
+                        cfg.get("cmvn", {}).get("norm_var", True))
+    x = F.relu(F.linear(x, sd["preprocessing.out.0.weight"], sd["preprocessing.out.0.bias"]))
+    bb = cfg["backbone"]
+    if bb["type"] == "mdtc":
+        x, new_cache = _mdtc(x, cache, sd, bb)
+    elif bb["type"] == "tcn":
+        x, new_cache = _tcn(x, cache, sd, bb)
+    elif bb["type"] == "gru":
+        x, new_cache = _gru(x, cache, sd, bb, cfg["hidden_dim"])
+    else:
+        raise ValueError("oracle: unsupported backbone " + str(bb["type"]))
+    x = F.linear(x, sd["classifier.linear.weight"], sd["classifier.linear.bias"])
+    if cfg.get("activation", {}).get("type", "sigmoid") != "identity":
+        x = torch.sigmoid(x)
+    if softmax:
+        x = x.softmax(2)
+    return x, new_cache

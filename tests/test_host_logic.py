@@ -1,0 +1,153 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every declared symbol,
+BN folding + weight packing (evaluated independently of the kernels), the drop-in Python
+surface (state_dict schema, init parity, error behaviour), and the front-end constants."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kws_oracle as O
+from tests import packed_eval as PE
+from tests.cases import CASE_NAMES, build_model
+from tests.conftest import ROOT, golden, have_reference, reference_init_model
+from wekws_b200 import Fbank, init_model, model_config, synth
+from wekws_b200 import frontend
+
+
+def test_library_exports_every_declared_symbol(native):
+    hdr = open(os.path.join(ROOT, "include", "wekws_b200.h")).read()
+    declared = re.findall(r"^WEKWS_API [\w\s\*]+?\b(wekws_\w+)\(", hdr, flags=re.M)
+    assert len(declared) >= 18
+    assert sorted(declared) == sorted(native.SIGNATURES), "binding and header disagree"
+    lib = C.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported"
+    assert native.lib().wekws_abi_version() == native.ABI_VERSION
+
+
+def test_error_reporting_without_gpu(native):
+    lib = native.lib()
+    h = C.c_void_p()
+    bad = native.ModelConfig(backbone=9, idim=80, hdim=64, odim=1)
+    assert lib.wekws_model_create(C.byref(bad), C.byref(h)) == -1
+    assert "backbone" in native.last_error()
+    ok = native.ModelConfig(backbone=native.BACKBONE_MDTC, idim=80, hdim=64, odim=1, num_stack=4, stack_size=4,
+                            kernel_size=5, activation=1, norm_var=1)
+    assert lib.wekws_model_create(C.byref(ok), C.byref(h)) == 0
+    assert lib.wekws_model_padding(h) == 244
+    # forward before finalize -> state error, pack with nothing set -> names the missing tensor
+    assert lib.wekws_model_forward(h, None, None, None, None, 1, 1, 0, None) == -3
+    assert lib.wekws_model_pack(h) == -3
+    assert "preprocessing.out.0.weight" in native.last_error()
+    lib.wekws_model_destroy(h)
+    cfg = native.FbankConfig(16000, 300, 160, 512, 80, 0.97, 1, 1e-7)
+    w = torch.ones(400)
+    mel = torch.zeros(80, 256)
+    assert lib.wekws_fbank_create(C.byref(cfg), C.c_void_p(w.data_ptr()), C.c_void_p(mel.data_ptr()), C.byref(h)) == -1
+    assert "frame_length" in native.last_error()
+    assert lib.wekws_fbank_num_frames(None, 16000) == 98
+    assert lib.wekws_fbank_num_frames(None, 399) == 0
+
+
+@pytest.mark.parametrize("case", CASE_NAMES)
+def test_fold_and_pack_reproduce_the_oracle(case, native):
+    cfg, model, B = build_model(case, init_model)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    h = model._build_handle(finalize=False)          # host-only half of finalize
+    stream, vec = PE.read_packed(native, h)
+    bb = cfg["backbone"]
+    has_cmvn = model.global_cmvn is not None
+    sig = "activation" not in cfg
+    x = synth.features(B, 21, cfg["input_dim"], seed=3, cmvn_like=has_cmvn)
+    if bb["type"] == "gru":
+        h0 = torch.randn(bb["num_layers"], B, cfg["hidden_dim"], generator=torch.Generator().manual_seed(1))
+        y_ref, c_ref = O.kws_forward(sd, cfg, x, h0)
+        y, c = PE.eval_gru(vec, cfg["hidden_dim"], bb["num_layers"], cfg["input_dim"], cfg["output_dim"], sig,
+                           has_cmvn, x, h0)
+    else:
+        kind = "mdtc" if bb["type"] == "mdtc" else ("ds_tcn" if bb.get("ds") else "tcn")
+        K = bb.get("kernel_size", 8)
+        dils = [1] + [2 ** l for _ in range(bb["num_stack"]) for l in range(bb["stack_size"])] \
+            if kind == "mdtc" else [2 ** i for i in range(bb["num_layers"])]
+        P = model.backbone.padding
+        cache = torch.randn(B, model.hdim, P, generator=torch.Generator().manual_seed(2))
+        y_ref, c_ref = O.kws_forward(sd, cfg, x, cache)
+        y, c = PE.eval_conv(stream, vec, kind, model.hdim, cfg["input_dim"], cfg["output_dim"], K, dils,
+                            bb.get("stack_size", 1), sig, has_cmvn, x, cache)
+    assert (y - y_ref).abs().max() <= 2e-5 * max(1.0, float(y_ref.abs().max()))
+    assert (c - c_ref).abs().max() <= 2e-5 * max(1.0, float(c_ref.abs().max()))
+
+
+def test_state_dict_schema_and_init_match_reference_golden():
+    d = golden("init_digest")
+    for name in ("mdtc", "mdtc_small", "ds_tcn", "tcn", "gru"):
+        torch.manual_seed(777)
+        m = init_model(model_config(name))
+        assert len(m.state_dict()) == int(d[name + "_nkeys"])
+        # same module construction order => same RNG stream => bit-identical initial weights
+        assert abs(synth.state_digest(m) - float(d[name])) <= 1e-9 * float(d[name])
+    m = init_model(model_config("mdtc"))
+    assert m.backbone.padding == 244 and m.hdim == 64 and m.idim == 80 and m.odim == 1
+    assert init_model(model_config("ds_tcn")).backbone.padding == 105
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", ["mdtc", "mdtc_small", "ds_tcn", "tcn", "gru"])
+def test_checkpoints_interchange_with_live_reference(name, tmp_path):
+    ref_init = reference_init_model()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_init(model_config(name))
+    ours = init_model(model_config(name))
+    synth.randomize_(ref, seed=5)
+    path = str(tmp_path / "ckpt.pt")
+    torch.save(ref.state_dict(), path)                      # utils/checkpoint.py:46-50
+    missing = ours.load_state_dict(torch.load(path), strict=True)   # utils/checkpoint.py:30
+    assert not missing.missing_keys and not missing.unexpected_keys
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    # average_model.py:77-83 turns num_batches_tracked into float: loading must still work
+    avg = {k: (v.float() if v.dtype == torch.int64 else v) for k, v in ref.state_dict().items()}
+    ours.load_state_dict(avg, strict=True)
+
+
+def test_unsupported_configs_and_cpu_inputs_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        init_model(dict(model_config("mdtc"), preprocessing=dict(type="cnn1d_s1")))
+    with pytest.raises(NotImplementedError):
+        init_model(dict(model_config("mdtc"), classifier=dict(type="global", dropout=0.5)))
+    with pytest.raises(SystemExit):                         # kws_model.py:124-125 behaviour
+        init_model(dict(model_config("mdtc"), preprocessing=dict(type="bogus")))
+    m = init_model(model_config("mdtc"))
+    with pytest.raises(RuntimeError, match="eval"):
+        m(torch.zeros(1, 4, 80))
+    m.eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4, 80))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Fbank(80)(torch.zeros(1, 16000))
+
+
+def test_frontend_constants_are_the_reference_tables():
+    g = golden("fbank")
+    assert np.array_equal(frontend.window_function("povey", 400).numpy(), g["povey_window"])
+    for nmel in (80, 40):
+        assert np.array_equal(frontend.mel_filterbank(nmel, 512, 16000.0).numpy(), g[f"mel{nmel}"])
+    mel = frontend.mel_filterbank(80, 512, 16000.0)
+    assert int((mel != 0).sum()) == 501 and int((mel != 0).sum(1).max()) <= 16
+    fb = Fbank(80)
+    assert fb.num_frames(16000) == 98 and fb.num_frames(399) == 0 and fb.num_frames(400) == 1
+    assert fb.n_fft == 512 and fb.win == 400 and fb.shift == 160
+
+
+def test_cmvn_loaders(tmp_path):
+    from wekws_b200 import load_cmvn, load_kaldi_cmvn
+    p = synth.write_cmvn_json(80, seed=7, path=str(tmp_path / "c.json"))
+    assert np.array_equal(load_cmvn(p), golden("cmvn")["cmvn"])
+    k = tmp_path / "kaldi_cmvn.txt"
+    k.write_text("<Nnet>\n<Splice> 6 2\n[ 0 1 2 ]\n<AddShift> 2 2\n<LearnRateCoef> 0 [ -1.5 -2.5 ]\n"
+                 "<Rescale> 2 2\n<LearnRateCoef> 0 [ 0.5 0.25 ]\n</Nnet>\n")
+    out = load_kaldi_cmvn(str(k))
+    assert out.shape == (2, 6) and np.allclose(out[0, :2], [1.5, 2.5]) and np.allclose(out[1, :2], [0.5, 0.25])

@@ -1,0 +1,95 @@
+"""Pins the CPU oracle (oracle/kws_oracle.py) to the reference: golden vectors produced by the
+real reference (oracle/make_golden.py) and, when /root/reference is present, the live code."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kws_oracle as O
+from tests.cases import CASE_NAMES, CHUNKS, build_model
+from tests.conftest import golden, have_reference, reference_init_model
+from wekws_b200 import init_model, synth
+
+TOL_MODEL = 2e-6      # oracle uses the same ATen ops as the reference: agreement is ~1 ulp
+TOL_FBANK = 2e-5      # same ops (rfft, mm) -- identical up to thread-count dependent summation order
+
+
+def _oracle_model(case):
+    # weights come from the product's holder modules (same state_dict schema as the reference);
+    # the digest check proves they are the weights the golden was generated with
+    cfg, model, B = build_model(case, init_model)
+    return cfg, {k: v.clone() for k, v in model.state_dict().items()}, model, B
+
+
+@pytest.mark.parametrize("case", CASE_NAMES)
+def test_oracle_matches_reference_golden(case):
+    g = golden("model_" + case)
+    cfg, sd, model, B = _oracle_model(case)
+    assert abs(synth.state_digest(model) - float(g["digest"])) < 1e-6 * float(g["digest"])
+    assert sorted(sd.keys()) == list(g["keys"])
+    gru = cfg["backbone"]["type"] == "gru"
+    cache = torch.zeros(cfg["backbone"]["num_layers"], B, cfg["hidden_dim"]) if gru else None
+    for i, T in enumerate(CHUNKS):
+        x = torch.from_numpy(g[f"x{i}"])
+        assert x.shape[1] == T
+        y, cache = O.kws_forward(sd, cfg, x, cache)
+        assert np.abs(y.numpy() - g[f"y{i}"]).max() <= TOL_MODEL * max(1.0, np.abs(g[f"y{i}"]).max())
+        if f"c{i}" in g:
+            assert np.abs(cache.numpy() - g[f"c{i}"]).max() <= 1e-5
+    full = torch.cat([torch.from_numpy(g[f"x{i}"]) for i in range(len(CHUNKS))], dim=1)
+    c0 = torch.zeros(cfg["backbone"]["num_layers"], B, cfg["hidden_dim"]) if gru else None
+    yf, _ = O.kws_forward(sd, cfg, full, c0)
+    assert np.abs(yf.numpy() - g["y_full"]).max() <= TOL_MODEL * max(1.0, np.abs(g["y_full"]).max())
+
+
+def test_oracle_fbank_matches_reference_golden():
+    g = golden("fbank")
+    names = [k[4:] for k in g.files if k.startswith("wav_")]
+    assert len(names) >= 9
+    for name in names:
+        wav = torch.from_numpy(g["wav_" + name])
+        for nmel in (80, 40):
+            ref = g[f"fbank{nmel}_{name}"]
+            out = O.fbank(wav, num_mel_bins=nmel).numpy()
+            assert out.shape == ref.shape, name
+            if ref.size:
+                assert np.abs(out - ref).max() <= TOL_FBANK, (name, nmel, np.abs(out - ref).max())
+    ham = O.fbank(torch.from_numpy(g["wav_gauss3000_a"]), window_type="hamming").numpy()
+    assert np.abs(ham - g["fbank80_hamming_gauss3000_a"]).max() <= TOL_FBANK
+    # all-zero audio gives exactly log(eps) in every bin
+    z = O.fbank(torch.zeros(1200)).numpy()
+    assert np.all(z == np.float32(np.log(np.float32(O.EPS))))
+
+
+def test_oracle_cmvn_loader_matches_golden(tmp_path):
+    p = synth.write_cmvn_json(80, seed=7, path=str(tmp_path / "cmvn.json"))
+    mean, istd = O.load_cmvn_json(p)
+    ref = golden("cmvn")["cmvn"]
+    assert np.allclose(mean.numpy(), ref[0].astype(np.float32), rtol=0, atol=0)
+    assert np.allclose(istd.numpy(), ref[1].astype(np.float32), rtol=0, atol=0)
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("case", CASE_NAMES)
+def test_oracle_matches_live_reference(case):
+    ref_init = reference_init_model()
+    cfg, ref, B = build_model(case, ref_init)
+    sd = ref.state_dict()
+    gru = cfg["backbone"]["type"] == "gru"
+    x = synth.features(B, 23, cfg["input_dim"], seed=5, cmvn_like=ref.global_cmvn is not None)
+    c_ref = torch.zeros(cfg["backbone"]["num_layers"], B, cfg["hidden_dim"]) if gru else torch.zeros(0, 0, 0)
+    c_or = c_ref if gru else None
+    with torch.no_grad():
+        for _ in range(3):
+            y_ref, c_ref = ref(x, c_ref)
+            y_or, c_or = O.kws_forward(sd, cfg, x, c_or)
+            assert (y_ref - y_or).abs().max() <= TOL_MODEL * max(1.0, float(y_ref.abs().max()))
+            assert (c_ref - c_or).abs().max() <= 1e-5
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")
+def test_oracle_fbank_matches_live_torchaudio():
+    import torchaudio.compliance.kaldi as kaldi
+    pcm = synth.pcm_int16(1, 16000 * 3, seed=77)[0].float()
+    ref = kaldi.fbank(pcm.unsqueeze(0), num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0,
+                      energy_floor=0.0, sample_frequency=16000)
+    assert (O.fbank(pcm) - ref).abs().max() <= TOL_FBANK

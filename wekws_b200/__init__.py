@@ -1,0 +1,17 @@
+"""wekws_b200 -- B200-native (sm_100a) streaming keyword-spotting forward path for WeKws.
+
+Public surface mirrors the reference (wenet-e2e/wekws):
+    init_model, KWSModel     <- wekws/model/kws_model.py
+    Fbank, fbank             <- torchaudio.compliance.kaldi.fbank as the reference calls it
+    load_cmvn, load_kaldi_cmvn <- wekws/utils/cmvn.py
+    patch_reference()        -> makes `wekws.model.kws_model` resolve to this implementation
+"""
+from .cmvn import load_cmvn, load_kaldi_cmvn
+from .configs import MODEL_NAMES, model_config
+from .frontend import Fbank, fbank
+from .kws_model import GlobalCMVN, KWSModel, init_model
+from .overlay import patch_reference
+
+__all__ = ["init_model", "KWSModel", "GlobalCMVN", "Fbank", "fbank", "load_cmvn", "load_kaldi_cmvn",
+           "model_config", "MODEL_NAMES", "patch_reference"]
+__version__ = "0.1.0"

@@ -1,0 +1,352 @@
+// Fused Kaldi-compatible log-mel filterbank (+ optional CMVN) for batches of PCM streams.
+//
+// Replaces torchaudio.compliance.kaldi.fbank as called from the reference
+// (wekws/dataset/processor.py:196-202, wekws/bin/stream_kws_ctc.py:354-360) and
+// GlobalCMVN.forward (wekws/model/cmvn.py:45-47): snip-edges framing (kaldi.py:44-83),
+// per-frame DC removal -> pre-emphasis with replicate padding -> window -> zero pad to 512
+// (kaldi.py:183-211), |rfft|^2 (kaldi.py:616-618), sparse triangular mel projection
+// (kaldi.py:436-511, 630), log(max(., eps)) (kaldi.py:633).
+//
+// One warp owns one frame.  The 512-point real FFT is a 256-point complex FFT of the
+// even/odd packed frame, done as a radix-8 / radix-8 / radix-4 Stockham autosort with the
+// first radix-8 entirely in registers (lane p holds z[p + 32 r]) and two exchanges through
+// bank-conflict-free padded per-warp shared buffers; lane-constant twiddles live in
+// registers.  A CTA (8 warps) stages the 1520 samples its 8 consecutive frames need once
+// (coalesced), so each PCM byte is read from HBM ~1.05x and each output byte written once.
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace wekws {
+
+namespace {
+
+constexpr int FB_WARPS = 8;                 // frames per CTA work item
+constexpr int FB_NT = FB_WARPS * 32;
+constexpr int WIN = 400, SHIFT = 160, NFFT = 512, NBIN = 256;
+constexpr int STAGE = (FB_WARPS - 1) * SHIFT + WIN;   // 1520 samples
+constexpr int A_SZ = 264, B_SZ = 280;       // padded exchange buffers (floats)
+constexpr int MAX_MEL = 128;
+
+struct FbankArgs {
+  const void* pcm;
+  const int32_t* lens;
+  const float* mean;
+  const float* istd;
+  float* out;
+  long long B, num_samples, pcm_stride, max_frames;
+  int nmel;
+  float preemph, log_floor;
+  int remove_dc;
+  // tables (device)
+  const float2* tw256;     // W_256^j
+  const float2* tw512;     // W_512^k, k < 256
+  const float* window;     // 400
+  const int* mstart;       // per mel bin: first fft bin, count, offset into mw
+  const int* mcnt;
+  const int* moff;
+  const float* mw;
+  int mw_total;
+};
+
+__device__ __forceinline__ int piA(int i) { return i + (i >> 5); }
+__device__ __forceinline__ int piB(int i) { return i + 8 * (i >> 6); }
+
+__device__ __forceinline__ void cmul(float& re, float& im, float wr, float wi) {
+  const float t = re * wr - im * wi;
+  im = fmaf(re, wi, im * wr);
+  re = t;
+}
+
+// In-place 8-point DFT (forward, e^{-2 pi i rk/8}) of (r[], i[]).
+__device__ __forceinline__ void dft8(float (&r)[8], float (&i)[8]) {
+  const float b0r = r[0] + r[4], b0i = i[0] + i[4], b1r = r[0] - r[4], b1i = i[0] - i[4];
+  const float b2r = r[2] + r[6], b2i = i[2] + i[6], b3r = r[2] - r[6], b3i = i[2] - i[6];
+  const float b4r = r[1] + r[5], b4i = i[1] + i[5], b5r = r[1] - r[5], b5i = i[1] - i[5];
+  const float b6r = r[3] + r[7], b6i = i[3] + i[7], b7r = r[3] - r[7], b7i = i[3] - i[7];
+  // c1 = b1 - i b3, c3 = b1 + i b3   (-i (x+iy) = y - ix)
+  const float c0r = b0r + b2r, c0i = b0i + b2i, c2r = b0r - b2r, c2i = b0i - b2i;
+  const float c1r = b1r + b3i, c1i = b1i - b3r, c3r = b1r - b3i, c3i = b1i + b3r;
+  const float c4r = b4r + b6r, c4i = b4i + b6i, c6r = b4r - b6r, c6i = b4i - b6i;
+  const float c5r = b5r + b7i, c5i = b5i - b7r, c7r = b5r - b7i, c7i = b5i + b7r;
+  const float h = 0.70710678118654752440f;
+  // w1*c5, w1 = (1 - i)/sqrt2 ; w3*c7, w3 = (-1 - i)/sqrt2
+  const float t5r = h * (c5r + c5i), t5i = h * (c5i - c5r);
+  const float t7r = h * (c7i - c7r), t7i = -h * (c7r + c7i);
+  r[0] = c0r + c4r; i[0] = c0i + c4i; r[4] = c0r - c4r; i[4] = c0i - c4i;
+  r[1] = c1r + t5r; i[1] = c1i + t5i; r[5] = c1r - t5r; i[5] = c1i - t5i;
+  r[2] = c2r + c6i; i[2] = c2i - c6r; r[6] = c2r - c6i; i[6] = c2i + c6r;   // -i c6
+  r[3] = c3r + t7r; i[3] = c3i + t7i; r[7] = c3r - t7r; i[7] = c3i - t7i;
+}
+
+template <typename PCM>
+__global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
+  __shared__ float s_stage[STAGE];
+  __shared__ float s_bufA[FB_WARPS][2][A_SZ];
+  __shared__ float s_bufB[FB_WARPS][2][B_SZ];
+  __shared__ float2 s_tw512[NBIN];
+  __shared__ float2 s_win[WIN / 2];
+  __shared__ float s_mw[2 * NBIN + 64];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < NBIN; i += FB_NT) s_tw512[i] = a.tw512[i];
+  for (int i = tid; i < WIN / 2; i += FB_NT) s_win[i] = make_float2(a.window[2 * i], a.window[2 * i + 1]);
+  for (int i = tid; i < a.mw_total; i += FB_NT) s_mw[i] = a.mw[i];
+
+  // lane-constant twiddles: pass 1 W_256^(lane k), pass 2 W_32^(p k) = W_256^(8 p k), p = lane/8
+  float t1r[8], t1i[8], t2r[8], t2i[8];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const float2 w1 = a.tw256[lane * k];
+    const float2 w2 = a.tw256[8 * (lane >> 3) * k];
+    t1r[k] = w1.x; t1i[k] = w1.y; t2r[k] = w2.x; t2i[k] = w2.y;
+  }
+
+  float* Ar = s_bufA[warp][0]; float* Ai = s_bufA[warp][1];
+  float* Br = s_bufB[warp][0]; float* Bi = s_bufB[warp][1];
+
+  const long long nfb = (a.max_frames + FB_WARPS - 1) / FB_WARPS;
+  const long long items = a.B * nfb;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long b = item / nfb;
+    const long long f0 = (item - b * nfb) * FB_WARPS;
+    long long len = a.lens ? (long long)a.lens[b] : a.num_samples;
+    if (len > a.num_samples) len = a.num_samples;
+    long long mb = len < WIN ? 0 : 1 + (len - WIN) / SHIFT;
+    if (mb > a.max_frames) mb = a.max_frames;
+
+    __syncthreads();
+    {
+      const PCM* src = reinterpret_cast<const PCM*>(a.pcm) + b * a.pcm_stride;
+      const long long base = f0 * SHIFT;
+      for (int i = tid; i < STAGE; i += FB_NT) {
+        const long long n = base + i;
+        s_stage[i] = n < len ? (float)src[n] : 0.f;
+      }
+    }
+    __syncthreads();
+
+    const long long f = f0 + warp;
+    if (f >= a.max_frames) continue;          // warp-uniform; no block barrier below in this iteration
+    float* outp = a.out + (b * a.max_frames + f) * a.nmel;
+    if (f >= mb) {
+      for (int m = lane; m < a.nmel; m += 32) outp[m] = 0.f;
+      continue;
+    }
+
+    // ---- window: lane owns packed points m = lane + 32 i (even/odd sample pair 2m, 2m+1) ----
+    const float* s = s_stage + warp * SHIFT;
+    float xa[7], xb[7], xc[7];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int m = lane + 32 * i;
+      if (m < WIN / 2) {
+        xb[i] = s[2 * m]; xc[i] = s[2 * m + 1];
+        xa[i] = m > 0 ? s[2 * m - 1] : xb[i];          // replicate pad (kaldi.py:195)
+        sum += xb[i] + xc[i];
+      } else {
+        xa[i] = xb[i] = xc[i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = a.remove_dc ? sum / (float)WIN : 0.f;
+    float zr[8], zi[8];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int m = lane + 32 * i;
+      if (m < WIN / 2) {
+        const float2 w = s_win[m];
+        const float pa = xa[i] - mean, pb = xb[i] - mean, pc = xc[i] - mean;
+        zr[i] = (pb - a.preemph * pa) * w.x;
+        zi[i] = (pc - a.preemph * pb) * w.y;
+      } else {
+        zr[i] = 0.f; zi[i] = 0.f;
+      }
+    }
+    zr[7] = 0.f; zi[7] = 0.f;
+
+    // ---- pass 1: radix 8 over r (n=256, s=1) -> A[8p + k] * W_256^(pk) ----
+    dft8(zr, zi);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k) cmul(zr[k], zi[k], t1r[k], t1i[k]);
+      const int idx = piA(8 * lane + k);
+      Ar[idx] = zr[k]; Ai[idx] = zi[k];
+    }
+    __syncwarp();
+    // ---- pass 2: radix 8 (n=32, s=8): j = q + 8p reads A[j + 32r], writes B[q + 64p + 8k] ----
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = piA(lane + 32 * r);
+      zr[r] = Ar[idx]; zi[r] = Ai[idx];
+    }
+    dft8(zr, zi);
+    {
+      const int q = lane & 7, p = lane >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k) cmul(zr[k], zi[k], t2r[k], t2i[k]);
+        const int idx = piB(q + 64 * p + 8 * k);
+        Br[idx] = zr[k]; Bi[idx] = zi[k];
+      }
+    }
+    __syncwarp();
+    // ---- pass 3: radix 4 (n=4, s=64): q reads B[q + 64r], writes Z[q + 64k] into A ----
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int q = lane + 32 * hh;
+      float r0 = Br[piB(q)], i0 = Bi[piB(q)];
+      float r1 = Br[piB(q + 64)], i1 = Bi[piB(q + 64)];
+      float r2 = Br[piB(q + 128)], i2 = Bi[piB(q + 128)];
+      float r3 = Br[piB(q + 192)], i3 = Bi[piB(q + 192)];
+      const float s0r = r0 + r2, s0i = i0 + i2, d0r = r0 - r2, d0i = i0 - i2;
+      const float s1r = r1 + r3, s1i = i1 + i3, d1r = r1 - r3, d1i = i1 - i3;
+      Ar[piA(q)] = s0r + s1r;        Ai[piA(q)] = s0i + s1i;
+      Ar[piA(q + 64)] = d0r + d1i;   Ai[piA(q + 64)] = d0i - d1r;     // d0 - i d1
+      Ar[piA(q + 128)] = s0r - s1r;  Ai[piA(q + 128)] = s0i - s1i;
+      Ar[piA(q + 192)] = d0r - d1i;  Ai[piA(q + 192)] = d0i + d1r;    // d0 + i d1
+    }
+    __syncwarp();
+    // ---- real-FFT untangle + power spectrum -> Br[0..255] ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = lane + 32 * i;
+      const int kn = (NBIN - k) & (NBIN - 1);
+      const float ar = Ar[piA(k)], ai = Ai[piA(k)];
+      const float cr = Ar[piA(kn)], ci = Ai[piA(kn)];
+      const float er = 0.5f * (ar + cr), ei = 0.5f * (ai - ci);
+      const float dr = 0.5f * (ar - cr), di = 0.5f * (ai + ci);
+      const float2 w = s_tw512[k];
+      const float p = w.x * dr - w.y * di, q = w.x * di + w.y * dr;
+      const float xr = er + q, xi = ei - p;
+      Br[k] = xr * xr + xi * xi;
+    }
+    __syncwarp();
+    // ---- mel projection (sparse rows), log floor, CMVN ----
+    for (int m = lane; m < a.nmel; m += 32) {
+      const int st = __ldg(a.mstart + m), cnt = __ldg(a.mcnt + m);
+      const float* w = s_mw + __ldg(a.moff + m);
+      float e = 0.f;
+      for (int i = 0; i < cnt; ++i) e = fmaf(w[i], Br[st + i], e);
+      float v = logf(fmaxf(e, a.log_floor));
+      if (a.mean) v -= __ldg(a.mean + m);
+      if (a.istd) v *= __ldg(a.istd + m);
+      outp[m] = v;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+}  // namespace wekws
+
+// ------------------------------------------------------------------------------- C ABI
+using namespace wekws;
+
+struct wekws_fbank {
+  wekws_fbank_config cfg;
+  int device = 0;
+  float2* d_tw256 = nullptr;
+  float2* d_tw512 = nullptr;
+  float* d_window = nullptr;
+  int* d_mstart = nullptr;
+  int* d_mcnt = nullptr;
+  int* d_moff = nullptr;
+  float* d_mw = nullptr;
+  int mw_total = 0;
+};
+
+extern "C" int wekws_fbank_create(const wekws_fbank_config* cfg, const float* h_window,
+                                  const float* h_mel, wekws_fbank** out) {
+  WEKWS_REQUIRE(cfg && h_window && h_mel && out, "wekws_fbank_create: null argument");
+  WEKWS_REQUIRE(cfg->frame_length == WIN && cfg->frame_shift == SHIFT && cfg->n_fft == NFFT,
+                "fbank: only frame_length=400, frame_shift=160, n_fft=512 are implemented (got %d/%d/%d)",
+                cfg->frame_length, cfg->frame_shift, cfg->n_fft);
+  WEKWS_REQUIRE(cfg->num_mel_bins >= 1 && cfg->num_mel_bins <= MAX_MEL, "fbank: num_mel_bins %d out of range",
+                cfg->num_mel_bins);
+  std::vector<float2> tw256(256), tw512(256);
+  const double PI = 3.14159265358979323846;
+  for (int j = 0; j < 256; ++j) {
+    tw256[j] = make_float2((float)cos(2 * PI * j / 256), (float)-sin(2 * PI * j / 256));
+    tw512[j] = make_float2((float)cos(2 * PI * j / 512), (float)-sin(2 * PI * j / 512));
+  }
+  const int nm = cfg->num_mel_bins;
+  std::vector<int> mstart(nm), mcnt(nm), moff(nm);
+  std::vector<float> mw;
+  for (int m = 0; m < nm; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < NBIN; ++k)
+      if (h_mel[m * NBIN + k] != 0.f) { if (first < 0) first = k; last = k; }
+    mstart[m] = first < 0 ? 0 : first;
+    mcnt[m] = first < 0 ? 0 : last - first + 1;
+    moff[m] = (int)mw.size();
+    for (int k = 0; k < mcnt[m]; ++k) mw.push_back(h_mel[m * NBIN + mstart[m] + k]);
+  }
+  WEKWS_REQUIRE(mw.size() <= 2 * NBIN + 64, "fbank: mel filterbank has %zu non-zeros, more than the %d supported",
+                mw.size(), 2 * NBIN + 64);
+  if (mw.empty()) mw.push_back(0.f);
+  wekws_fbank* fb = new (std::nothrow) wekws_fbank();
+  if (!fb) { set_error("out of host memory"); return WEKWS_ERR_NOMEM; }
+  fb->cfg = *cfg;
+  fb->mw_total = (int)mw.size();
+  WEKWS_CUDA_OK(cudaGetDevice(&fb->device));
+#define UP(dst, vec)                                                                      \
+  WEKWS_CUDA_OK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                   \
+  WEKWS_CUDA_OK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+  UP(fb->d_tw256, tw256) UP(fb->d_tw512, tw512) UP(fb->d_mstart, mstart) UP(fb->d_mcnt, mcnt)
+  UP(fb->d_moff, moff) UP(fb->d_mw, mw)
+#undef UP
+  WEKWS_CUDA_OK(cudaMalloc((void**)&fb->d_window, WIN * sizeof(float)));
+  WEKWS_CUDA_OK(cudaMemcpy(fb->d_window, h_window, WIN * sizeof(float), cudaMemcpyHostToDevice));
+  *out = fb;
+  return WEKWS_OK;
+}
+
+extern "C" void wekws_fbank_destroy(wekws_fbank* fb) {
+  if (!fb) return;
+  cudaFree(fb->d_tw256); cudaFree(fb->d_tw512); cudaFree(fb->d_window);
+  cudaFree(fb->d_mstart); cudaFree(fb->d_mcnt); cudaFree(fb->d_moff); cudaFree(fb->d_mw);
+  delete fb;
+}
+
+extern "C" int64_t wekws_fbank_num_frames(const wekws_fbank* fb, int64_t num_samples) {
+  const int win = fb ? fb->cfg.frame_length : WIN, shift = fb ? fb->cfg.frame_shift : SHIFT;
+  return num_samples < win ? 0 : 1 + (num_samples - win) / shift;
+}
+
+extern "C" int wekws_fbank_num_mel_bins(const wekws_fbank* fb) { return fb ? fb->cfg.num_mel_bins : 0; }
+
+extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_dtype, int64_t B,
+                                   int64_t num_samples, int64_t pcm_stride, const int32_t* d_lens,
+                                   const float* d_mean, const float* d_istd, float* d_out,
+                                   int64_t max_frames, void* stream) {
+  WEKWS_REQUIRE(fb && d_out, "wekws_fbank_forward: null handle or output");
+  WEKWS_REQUIRE(B >= 0 && num_samples >= 0 && max_frames >= 0, "wekws_fbank_forward: negative size");
+  WEKWS_REQUIRE(pcm_dtype == WEKWS_PCM_S16 || pcm_dtype == WEKWS_PCM_F32, "wekws_fbank_forward: bad pcm_dtype %d", pcm_dtype);
+  WEKWS_REQUIRE(max_frames >= wekws_fbank_num_frames(fb, num_samples) || d_lens,
+                "wekws_fbank_forward: max_frames %lld < frames of %lld samples", (long long)max_frames,
+                (long long)num_samples);
+  if (B == 0 || max_frames == 0) return WEKWS_OK;
+  WEKWS_REQUIRE(d_pcm, "wekws_fbank_forward: null pcm");
+  FbankArgs a;
+  a.pcm = d_pcm; a.lens = d_lens; a.mean = d_mean; a.istd = d_istd; a.out = d_out;
+  a.B = B; a.num_samples = num_samples; a.pcm_stride = pcm_stride; a.max_frames = max_frames;
+  a.nmel = fb->cfg.num_mel_bins; a.preemph = fb->cfg.preemphasis; a.log_floor = fb->cfg.log_floor;
+  a.remove_dc = fb->cfg.remove_dc;
+  a.tw256 = fb->d_tw256; a.tw512 = fb->d_tw512; a.window = fb->d_window;
+  a.mstart = fb->d_mstart; a.mcnt = fb->d_mcnt; a.moff = fb->d_moff; a.mw = fb->d_mw;
+  a.mw_total = fb->mw_total;
+  const long long items = B * ((max_frames + FB_WARPS - 1) / FB_WARPS);
+  const long long cap = (long long)device_sm_count() * 4;
+  const int grid = (int)(items < cap ? items : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pcm_dtype == WEKWS_PCM_S16)
+    fbank_kernel<int16_t><<<grid, FB_NT, 0, st>>>(a);
+  else
+    fbank_kernel<float><<<grid, FB_NT, 0, st>>>(a);
+  return check_launch("fbank_kernel");
+}

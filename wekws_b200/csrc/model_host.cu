@@ -1,0 +1,465 @@
+// Host side of the model C-ABI: tensor registry keyed by the reference's state_dict names,
+// eval-mode BatchNorm folding, weight packing for the fused kernels, forward dispatch.
+//
+// Folding (SURVEY.md 8a "Folded per-block math"; mdtc.py:55-59,115-118; tcn.py:75-84,101-114):
+// for each BatchNorm with s = gamma / sqrt(var + 1e-5), t = beta - mean * s,
+//     BN(conv(x; W, b)) = conv(x; W * s[out], b * s + t)
+// computed in double and rounded once to fp32.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_backbone.h"
+#include "gru.h"
+
+namespace wekws {
+
+static thread_local std::string tl_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  tl_error = buf;
+}
+
+int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+namespace {
+
+__global__ void softmax_rows_kernel(float* x, long long rows, int n) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* p = x + row * n;
+  float m = -INFINITY;
+  for (int i = lane; i < n; i += 32) m = fmaxf(m, p[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s += expf(p[i] - m);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int i = lane; i < n; i += 32) p[i] = expf(p[i] - m) / s;
+}
+
+struct Folded {           // BN as per-channel scale/shift
+  std::vector<double> s, t;
+};
+
+}  // namespace
+}  // namespace wekws
+
+using namespace wekws;
+
+struct wekws_model {
+  wekws_model_config cfg;
+  std::map<std::string, std::vector<float>> tensors;
+  bool finalized = false;
+  int device = 0;
+  int padding = 0, padmax = 0, nblocks = 0;
+  bool has_cmvn = false;
+  std::vector<int> dil, coff;
+  std::vector<float> h_stream, h_vec;
+  std::vector<int> h_chunk_off;
+  float* d_stream = nullptr;
+  float* d_vec = nullptr;
+  int* d_chunk_off = nullptr;
+  ConvArgs conv{};
+  GruArgs gru{};
+  int conv_max_T = 0;
+};
+
+namespace {
+
+int get_tensor(const wekws_model* m, const std::string& name, size_t numel, const float** out) {
+  auto it = m->tensors.find(name);
+  if (it == m->tensors.end()) {
+    set_error("finalize: tensor '%s' was never set", name.c_str());
+    return WEKWS_ERR_STATE;
+  }
+  if (it->second.size() != numel) {
+    set_error("finalize: tensor '%s' has %zu elements, expected %zu", name.c_str(), it->second.size(), numel);
+    return WEKWS_ERR_INVALID;
+  }
+  *out = it->second.data();
+  return WEKWS_OK;
+}
+
+#define GET(ptr, name, numel)                                            \
+  const float* ptr = nullptr;                                            \
+  do { int _rc = get_tensor(m, (name), (numel), &ptr); if (_rc) return _rc; } while (0)
+
+int fold_bn(const wekws_model* m, const std::string& p, int C, Folded* f) {
+  GET(g, p + ".weight", (size_t)C);
+  GET(b, p + ".bias", (size_t)C);
+  GET(mu, p + ".running_mean", (size_t)C);
+  GET(var, p + ".running_var", (size_t)C);
+  f->s.resize(C); f->t.resize(C);
+  for (int c = 0; c < C; ++c) {
+    const double s = (double)g[c] / sqrt((double)var[c] + 1e-5);
+    f->s[c] = s;
+    f->t[c] = (double)b[c] - (double)mu[c] * s;
+  }
+  return WEKWS_OK;
+}
+
+size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
+
+// Appends W^T (K x C, from W[o][c] * s[o] with arbitrary source strides) as row chunks.
+void push_gemm(wekws_model* m, int K, int C, const float* W, size_t o_stride, size_t c_stride, const double* s) {
+  const int KC = conv_chunk_rows(C);
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    const int kk = K - k0 < KC ? K - k0 : KC;
+    m->h_chunk_off.push_back((int)m->h_stream.size());
+    for (int k = k0; k < k0 + kk; ++k)
+      for (int o = 0; o < C; ++o)
+        m->h_stream.push_back((float)((double)W[o * o_stride + k * c_stride] * (s ? s[o] : 1.0)));
+  }
+}
+
+int pack_common_front(wekws_model* m, int* v_mean, int* v_istd) {
+  const int idim = m->cfg.idim;
+  m->has_cmvn = m->tensors.count("global_cmvn.mean") != 0;
+  *v_mean = (int)m->h_vec.size();
+  m->h_vec.resize(m->h_vec.size() + pad4(idim), 0.f);
+  *v_istd = (int)m->h_vec.size();
+  m->h_vec.resize(m->h_vec.size() + pad4(idim), 1.f);
+  if (m->has_cmvn) {
+    GET(mean, "global_cmvn.mean", (size_t)idim);
+    GET(istd, "global_cmvn.istd", (size_t)idim);
+    for (int k = 0; k < idim; ++k) {
+      m->h_vec[*v_mean + k] = mean[k];
+      m->h_vec[*v_istd + k] = m->cfg.norm_var ? istd[k] : 1.f;   // cmvn.py:46-47
+    }
+  }
+  return WEKWS_OK;
+}
+
+int pack_classifier(wekws_model* m, int H, int* v_wc, int* v_bc) {
+  const int odim = m->cfg.odim;
+  GET(wc, "classifier.linear.weight", (size_t)odim * H);
+  GET(bc, "classifier.linear.bias", (size_t)odim);
+  *v_wc = (int)m->h_vec.size();
+  m->h_vec.resize(m->h_vec.size() + pad4((size_t)H * odim), 0.f);
+  for (int c = 0; c < H; ++c)
+    for (int j = 0; j < odim; ++j) m->h_vec[*v_wc + c * odim + j] = wc[j * H + c];
+  *v_bc = (int)m->h_vec.size();
+  m->h_vec.resize(m->h_vec.size() + pad4(odim), 0.f);
+  for (int j = 0; j < odim; ++j) m->h_vec[*v_bc + j] = bc[j];
+  return WEKWS_OK;
+}
+
+int pack_conv(wekws_model* m) {
+  const wekws_model_config& c = m->cfg;
+  const int C = c.hdim, K = c.kernel_size, idim = c.idim;
+  WEKWS_REQUIRE(C == 32 || C == 64 || C == 128 || C == 256, "hidden_dim %d unsupported (32/64/128/256)", C);
+  WEKWS_REQUIRE(K >= 2 && K <= 8, "kernel_size %d unsupported (2..8)", K);
+  WEKWS_REQUIRE(idim >= 1 && idim <= 128, "input_dim %d unsupported (1..128)", idim);
+  std::vector<std::string> prefix;
+  m->dil.clear(); m->coff.clear();
+  if (c.backbone == WEKWS_BACKBONE_MDTC) {
+    WEKWS_REQUIRE(c.num_stack >= 1 && c.stack_size >= 1, "mdtc: num_stack/stack_size must be >= 1");
+    prefix.push_back("backbone.preprocessor");
+    m->dil.push_back(1);
+    for (int s = 0; s < c.num_stack; ++s)
+      for (int l = 0; l < c.stack_size; ++l) {
+        prefix.push_back("backbone.blocks." + std::to_string(s) + ".res_blocks." + std::to_string(l));
+        m->dil.push_back(1 << l);
+      }
+  } else {
+    WEKWS_REQUIRE(c.num_layers >= 1, "tcn: num_layers must be >= 1");
+    for (int i = 0; i < c.num_layers; ++i) {
+      prefix.push_back("backbone.network." + std::to_string(i) + ".cnn");
+      m->dil.push_back(1 << i);
+    }
+  }
+  m->nblocks = (int)prefix.size();
+  WEKWS_REQUIRE(m->nblocks <= kMaxBlocks, "%d blocks exceed the supported %d", m->nblocks, kMaxBlocks);
+  m->padding = 0; m->padmax = 0;
+  for (int b = 0; b < m->nblocks; ++b) {
+    m->coff.push_back(m->padding);
+    const int pad = m->dil[b] * (K - 1);
+    m->padding += pad;
+    if (pad > m->padmax) m->padmax = pad;
+  }
+  m->h_stream.clear(); m->h_vec.clear(); m->h_chunk_off.clear();
+  ConvArgs& a = m->conv;
+  memset(&a, 0, sizeof(a));
+  int rc = pack_common_front(m, &a.v_mean, &a.v_istd);
+  if (rc) return rc;
+  // preprocessing Linear (subsampling.py:45-48): W (C, idim)
+  {
+    GET(w, "preprocessing.out.0.weight", (size_t)C * idim);
+    GET(b, "preprocessing.out.0.bias", (size_t)C);
+    push_gemm(m, idim, C, w, idim, 1, nullptr);
+    a.v_bp = (int)m->h_vec.size();
+    m->h_vec.insert(m->h_vec.end(), b, b + C);
+  }
+  a.v_blocks = (int)m->h_vec.size();
+  a.v_blk_stride = c.backbone == WEKWS_BACKBONE_MDTC ? (K + 3) * C
+                 : c.backbone == WEKWS_BACKBONE_DSTCN ? (K + 2) * C : C;
+  for (int bi = 0; bi < m->nblocks; ++bi) {
+    const std::string& p = prefix[bi];
+    const size_t v0 = m->h_vec.size();
+    if (c.backbone == WEKWS_BACKBONE_MDTC || c.backbone == WEKWS_BACKBONE_DSTCN) {
+      const bool md = c.backbone == WEKWS_BACKBONE_MDTC;
+      const std::string dw = md ? p + ".conv1.conv" : p + ".0";
+      const std::string dwbn = md ? p + ".conv1.bn" : p + ".1";
+      const std::string pw = md ? p + ".conv1.pointwise" : p + ".3";
+      const std::string pwbn = md ? p + ".bn1" : p + ".4";
+      GET(wd, dw + ".weight", (size_t)C * K);
+      GET(bd, dw + ".bias", (size_t)C);
+      Folded f0, f1;
+      if ((rc = fold_bn(m, dwbn, C, &f0))) return rc;
+      if ((rc = fold_bn(m, pwbn, C, &f1))) return rc;
+      for (int j = 0; j < K; ++j)
+        for (int ch = 0; ch < C; ++ch) m->h_vec.push_back((float)((double)wd[ch * K + j] * f0.s[ch]));
+      for (int ch = 0; ch < C; ++ch) m->h_vec.push_back((float)((double)bd[ch] * f0.s[ch] + f0.t[ch]));
+      GET(w1, pw + ".weight", (size_t)C * C);
+      GET(b1, pw + ".bias", (size_t)C);
+      push_gemm(m, C, C, w1, C, 1, f1.s.data());
+      for (int o = 0; o < C; ++o) m->h_vec.push_back((float)((double)b1[o] * f1.s[o] + f1.t[o]));
+      if (md) {
+        Folded f2;
+        if ((rc = fold_bn(m, p + ".bn2", C, &f2))) return rc;
+        GET(w2, p + ".conv2.weight", (size_t)C * C);
+        GET(b2, p + ".conv2.bias", (size_t)C);
+        push_gemm(m, C, C, w2, C, 1, f2.s.data());
+        for (int o = 0; o < C; ++o) m->h_vec.push_back((float)((double)b2[o] * f2.s[o] + f2.t[o]));
+      }
+    } else {  // dense TCN: weight (C, C, K) -> K tap matrices
+      GET(w, p + ".0.weight", (size_t)C * C * K);
+      GET(b, p + ".0.bias", (size_t)C);
+      Folded f;
+      if ((rc = fold_bn(m, p + ".1", C, &f))) return rc;
+      for (int j = 0; j < K; ++j) push_gemm(m, C, C, w + j, (size_t)C * K, K, f.s.data());
+      for (int o = 0; o < C; ++o) m->h_vec.push_back((float)((double)b[o] * f.s[o] + f.t[o]));
+    }
+    if (m->h_vec.size() - v0 != (size_t)a.v_blk_stride) {
+      set_error("internal: block vector stride mismatch");
+      return WEKWS_ERR_INVALID;
+    }
+  }
+  if ((rc = pack_classifier(m, C, &a.v_wc, &a.v_bc))) return rc;
+  m->h_chunk_off.push_back((int)m->h_stream.size());
+  a.kind = c.backbone; a.C = C; a.idim = idim; a.odim = c.odim; a.nblocks = m->nblocks; a.ktaps = K;
+  a.P = m->padding; a.stack_size = c.stack_size > 0 ? c.stack_size : 1; a.act = c.activation;
+  a.has_cmvn = m->has_cmvn ? 1 : 0;
+  a.n_chunks = (int)m->h_chunk_off.size() - 1;
+  for (int b = 0; b < m->nblocks; ++b) { a.dil[b] = m->dil[b]; a.coff[b] = m->coff[b]; }
+  return WEKWS_OK;
+}
+
+int pack_gru(wekws_model* m) {
+  const wekws_model_config& c = m->cfg;
+  const int H = c.hdim, G = 3 * H, idim = c.idim, L = c.num_layers;
+  WEKWS_REQUIRE(H == 128, "GRU hidden_dim %d unsupported (128 only)", H);
+  WEKWS_REQUIRE(L >= 1 && L <= 4, "GRU num_layers %d unsupported (1..4)", L);
+  WEKWS_REQUIRE(idim >= 1 && idim <= 128, "input_dim %d unsupported (1..128)", idim);
+  m->h_stream.clear(); m->h_vec.clear(); m->h_chunk_off.clear();
+  m->padding = 0; m->padmax = 0; m->nblocks = L;
+  GruArgs& a = m->gru;
+  memset(&a, 0, sizeof(a));
+  int rc = pack_common_front(m, &a.v_mean, &a.v_istd);
+  if (rc) return rc;
+  GET(wp, "preprocessing.out.0.weight", (size_t)H * idim);
+  GET(bp, "preprocessing.out.0.bias", (size_t)H);
+  a.v_wp = (int)m->h_vec.size();
+  for (int k = 0; k < idim; ++k)
+    for (int j = 0; j < H; ++j) m->h_vec.push_back(wp[j * idim + k]);
+  a.v_bp = (int)m->h_vec.size();
+  m->h_vec.insert(m->h_vec.end(), bp, bp + H);
+  a.v_layers = (int)m->h_vec.size();
+  a.v_layer_stride = 2 * H * G + 2 * G;
+  for (int l = 0; l < L; ++l) {
+    const std::string sfx = "_l" + std::to_string(l);
+    GET(wih, "backbone.weight_ih" + sfx, (size_t)G * H);
+    GET(whh, "backbone.weight_hh" + sfx, (size_t)G * H);
+    GET(bih, "backbone.bias_ih" + sfx, (size_t)G);
+    GET(bhh, "backbone.bias_hh" + sfx, (size_t)G);
+    for (int k = 0; k < H; ++k)
+      for (int g = 0; g < G; ++g) m->h_vec.push_back(wih[g * H + k]);
+    for (int k = 0; k < H; ++k)
+      for (int g = 0; g < G; ++g) m->h_vec.push_back(whh[g * H + k]);
+    m->h_vec.insert(m->h_vec.end(), bih, bih + G);
+    m->h_vec.insert(m->h_vec.end(), bhh, bhh + G);
+  }
+  if ((rc = pack_classifier(m, H, &a.v_wc, &a.v_bc))) return rc;
+  a.L = L; a.H = H; a.idim = idim; a.odim = c.odim; a.act = c.activation; a.has_cmvn = m->has_cmvn ? 1 : 0;
+  return WEKWS_OK;
+}
+
+void free_device(wekws_model* m) {
+  cudaFree(m->d_stream); cudaFree(m->d_vec); cudaFree(m->d_chunk_off);
+  m->d_stream = nullptr; m->d_vec = nullptr; m->d_chunk_off = nullptr;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------- C ABI
+extern "C" const char* wekws_last_error(void) { return tl_error.c_str(); }
+extern "C" int wekws_abi_version(void) { return WEKWS_B200_ABI_VERSION; }
+extern "C" uint64_t wekws_launch_count(void) { return g_launches.load(); }
+
+extern "C" int wekws_model_create(const wekws_model_config* cfg, wekws_model** out) {
+  WEKWS_REQUIRE(cfg && out, "wekws_model_create: null argument");
+  WEKWS_REQUIRE(cfg->backbone >= WEKWS_BACKBONE_MDTC && cfg->backbone <= WEKWS_BACKBONE_GRU,
+                "unknown backbone id %d", cfg->backbone);
+  WEKWS_REQUIRE(cfg->odim >= 1, "output_dim must be >= 1");
+  WEKWS_REQUIRE(cfg->activation == WEKWS_ACT_IDENTITY || cfg->activation == WEKWS_ACT_SIGMOID,
+                "unknown activation id %d", cfg->activation);
+  wekws_model* m = new (std::nothrow) wekws_model();
+  if (!m) { set_error("out of host memory"); return WEKWS_ERR_NOMEM; }
+  m->cfg = *cfg;
+  *out = m;
+  return WEKWS_OK;
+}
+
+extern "C" void wekws_model_destroy(wekws_model* m) {
+  if (!m) return;
+  free_device(m);
+  delete m;
+}
+
+extern "C" int wekws_model_padding(const wekws_model* m) {
+  if (!m) return 0;
+  if (m->cfg.backbone == WEKWS_BACKBONE_GRU) return 0;
+  int pad = 0;
+  const int K = m->cfg.kernel_size;
+  if (m->cfg.backbone == WEKWS_BACKBONE_MDTC) {
+    pad = K - 1;
+    for (int s = 0; s < m->cfg.num_stack; ++s)
+      for (int l = 0; l < m->cfg.stack_size; ++l) pad += (1 << l) * (K - 1);
+  } else {
+    for (int i = 0; i < m->cfg.num_layers; ++i) pad += (1 << i) * (K - 1);
+  }
+  return pad;
+}
+
+extern "C" int wekws_model_set_tensor(wekws_model* m, const char* name, const float* h_data, int64_t numel) {
+  WEKWS_REQUIRE(m && name && (h_data || numel == 0) && numel >= 0, "wekws_model_set_tensor: bad argument");
+  m->tensors[name].assign(h_data, h_data + numel);
+  m->finalized = false;
+  return WEKWS_OK;
+}
+
+extern "C" int wekws_model_pack(wekws_model* m) {
+  WEKWS_REQUIRE(m, "wekws_model_pack: null handle");
+  return m->cfg.backbone == WEKWS_BACKBONE_GRU ? pack_gru(m) : pack_conv(m);
+}
+
+extern "C" int wekws_model_finalize(wekws_model* m) {
+  WEKWS_REQUIRE(m, "wekws_model_finalize: null handle");
+  int rc = wekws_model_pack(m);
+  if (rc) return rc;
+  free_device(m);
+  WEKWS_CUDA_OK(cudaGetDevice(&m->device));
+  WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_vec, m->h_vec.size() * sizeof(float)));
+  WEKWS_CUDA_OK(cudaMemcpy(m->d_vec, m->h_vec.data(), m->h_vec.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (m->cfg.backbone != WEKWS_BACKBONE_GRU) {
+    WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_stream, m->h_stream.size() * sizeof(float)));
+    WEKWS_CUDA_OK(cudaMemcpy(m->d_stream, m->h_stream.data(), m->h_stream.size() * sizeof(float), cudaMemcpyHostToDevice));
+    WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_chunk_off, m->h_chunk_off.size() * sizeof(int)));
+    WEKWS_CUDA_OK(cudaMemcpy(m->d_chunk_off, m->h_chunk_off.data(), m->h_chunk_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    m->conv.wstream = m->d_stream; m->conv.chunk_off = m->d_chunk_off; m->conv.vec = m->d_vec;
+    m->conv_max_T = conv_backbone_max_T(m->conv, m->padmax);
+    WEKWS_REQUIRE(m->conv_max_T >= 1, "model does not fit the fused kernel's shared memory");
+  } else {
+    m->gru.vec = m->d_vec;
+  }
+  m->finalized = true;
+  return WEKWS_OK;
+}
+
+extern "C" int64_t wekws_model_packed_floats(const wekws_model* m, int which) {
+  if (!m) return 0;
+  return which == 0 ? (int64_t)m->h_stream.size() : (int64_t)m->h_vec.size();
+}
+
+extern "C" int wekws_model_packed_copy(const wekws_model* m, int which, float* h_dst, int64_t capacity) {
+  WEKWS_REQUIRE(m && h_dst, "wekws_model_packed_copy: null argument");
+  const std::vector<float>& v = which == 0 ? m->h_stream : m->h_vec;
+  WEKWS_REQUIRE((int64_t)v.size() <= capacity, "wekws_model_packed_copy: capacity too small");
+  memcpy(h_dst, v.data(), v.size() * sizeof(float));
+  return WEKWS_OK;
+}
+
+extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const float* d_in_cache,
+                                   float* d_out, float* d_out_cache, int64_t B, int64_t T,
+                                   uint32_t flags, void* stream) {
+  WEKWS_REQUIRE(m, "wekws_model_forward: null handle");
+  if (!m->finalized) { set_error("wekws_model_forward called before wekws_model_finalize"); return WEKWS_ERR_STATE; }
+  WEKWS_REQUIRE(B >= 0 && T >= 0 && B < (1 << 30) && T < (1 << 30), "wekws_model_forward: bad B/T");
+  if (B == 0 || T == 0) return WEKWS_OK;
+  WEKWS_REQUIRE(d_feats && d_out && d_out_cache, "wekws_model_forward: null tensor");
+  int dev = 0;
+  WEKWS_CUDA_OK(cudaGetDevice(&dev));
+  WEKWS_REQUIRE(dev == m->device, "model was finalized on device %d but current device is %d", m->device, dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->cfg.backbone == WEKWS_BACKBONE_GRU) {
+    GruArgs a = m->gru;
+    a.feats = d_feats; a.in_cache = d_in_cache; a.out = d_out; a.out_cache = d_out_cache;
+    a.B = (int)B; a.T = (int)T;
+    int rc = gru_launch(a, st);
+    if (rc) return rc;
+  } else {
+    // time-chunk long inputs; the cache carries the state between chunks exactly as in
+    // streaming use (chunked == full utterance, SURVEY.md 8a "Numerical facts")
+    const int maxT = m->conv_max_T;
+    const int nchunk = (int)((T + maxT - 1) / maxT);
+    const int Tc = (int)((T + nchunk - 1) / nchunk);
+    for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+      ConvArgs a = m->conv;
+      a.feats = d_feats + t0 * m->cfg.idim;
+      a.out = d_out + t0 * m->cfg.odim;
+      a.in_cache = t0 == 0 ? d_in_cache : d_out_cache;
+      a.out_cache = d_out_cache;
+      a.B = (int)B;
+      a.T = (int)(T - t0 < Tc ? T - t0 : Tc);
+      a.feat_bstride = T * m->cfg.idim;
+      a.out_bstride = T * m->cfg.odim;
+      int rc = conv_backbone_launch(a, m->padmax, st);
+      if (rc) return rc;
+    }
+  }
+  if (flags & WEKWS_FWD_SOFTMAX) {
+    const long long rows = B * T;
+    const int wpb = 8;
+    softmax_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_out, rows, m->cfg.odim);
+    int rc = check_launch("softmax_rows_kernel");
+    if (rc) return rc;
+  }
+  return WEKWS_OK;
+}
+
+extern "C" int wekws_pipeline_forward(wekws_fbank* fb, wekws_model* m, const void* d_pcm, int pcm_dtype,
+                                      int64_t B, int64_t num_samples, int64_t pcm_stride,
+                                      float* d_feat_scratch, const float* d_in_cache, float* d_out,
+                                      float* d_out_cache, uint32_t flags, void* stream) {
+  WEKWS_REQUIRE(fb && m && d_feat_scratch, "wekws_pipeline_forward: null argument");
+  WEKWS_REQUIRE(wekws_fbank_num_mel_bins(fb) == m->cfg.idim, "pipeline: fbank has %d mel bins but the model expects input_dim %d",
+                wekws_fbank_num_mel_bins(fb), m->cfg.idim);
+  const int64_t frames = wekws_fbank_num_frames(fb, num_samples);
+  int rc = wekws_fbank_forward(fb, d_pcm, pcm_dtype, B, num_samples, pcm_stride, nullptr, nullptr, nullptr,
+                               d_feat_scratch, frames, stream);
+  if (rc) return rc;
+  return wekws_model_forward(m, d_feat_scratch, d_in_cache, d_out, d_out_cache, B, frames, flags, stream);
+}

@@ -1,0 +1,315 @@
+"""Drop-in ``KWSModel`` / ``init_model`` for the reference's wekws/model/kws_model.py.
+
+Same constructor, attributes (``idim``, ``odim``, ``hdim``, ``backbone.padding``), the same
+``state_dict`` key set and shapes (so reference checkpoints load with ``strict=True`` and
+``wekws/bin/average_model.py`` output loads too), and the same call surface:
+
+    logits, out_cache = model(feats)               # wekws/bin/score.py:125
+    logits, cache     = model(feats, cache)        # wekws/bin/stream_kws_ctc.py:487
+
+The modules in here are parameter HOLDERS only.  ``forward`` hands raw device pointers to
+the C-ABI library (include/wekws_b200.h) whose fused sm_100a kernels do all the work:
+CMVN -> Linear+ReLU -> backbone with streaming cache -> classifier -> activation
+(kws_model.py:65-76).  There is no PyTorch / CPU fallback: CPU tensors, training mode or a
+missing native library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .cmvn import load_cmvn, load_kaldi_cmvn
+
+_EMPTY = torch.zeros(0, 0, 0, dtype=torch.float)
+
+
+def _holder(**children) -> nn.Module:
+    m = nn.Module()
+    for name, child in children.items():
+        m.add_module(name, child)
+    return m
+
+
+class GlobalCMVN(nn.Module):
+    """Buffers of wekws/model/cmvn.py:19-35; applied inside the fused kernel."""
+
+    def __init__(self, mean: torch.Tensor, istd: torch.Tensor, norm_var: bool = True):
+        super().__init__()
+        assert mean.shape == istd.shape
+        self.norm_var = norm_var
+        self.register_buffer("mean", mean)
+        self.register_buffer("istd", istd)
+
+
+def _linear_subsampling(idim: int, odim: int) -> nn.Module:
+    """state_dict: out.0.{weight,bias} (subsampling.py:45-48)."""
+    m = _holder(out=nn.Sequential(nn.Linear(idim, odim), nn.ReLU()))
+    m.subsampling_rate = 1
+    return m
+
+
+def _mdtc_block(ch: int, k: int, d: int) -> nn.Module:
+    """conv1.{conv,bn,pointwise}, bn1, conv2, bn2 (mdtc.py:37-53, 79-92)."""
+    blk = _holder(
+        conv1=_holder(conv=nn.Conv1d(ch, ch, k, dilation=d, groups=ch), bn=nn.BatchNorm1d(ch),
+                      pointwise=nn.Conv1d(ch, ch, 1)),
+        bn1=nn.BatchNorm1d(ch), conv2=nn.Conv1d(ch, ch, 1), bn2=nn.BatchNorm1d(ch))
+    blk.padding = d * (k - 1)
+    return blk
+
+
+def _mdtc(num_stack: int, stack_size: int, ch: int, k: int) -> nn.Module:
+    """preprocessor + blocks.{s}.res_blocks.{l} with dilations 2**l (mdtc.py:151-156, 226-238)."""
+    assert k % 2 == 1
+    pre = _mdtc_block(ch, k, 1)
+    stacks = nn.ModuleList()
+    padding = pre.padding
+    for _ in range(num_stack):
+        res = nn.ModuleList([_mdtc_block(ch, k, 2 ** l) for l in range(stack_size)])
+        st = _holder(res_blocks=res)
+        st.padding = sum(b.padding for b in res)
+        padding += st.padding
+        stacks.append(st)
+    bb = _holder(preprocessor=pre, blocks=stacks)
+    bb.padding = padding
+    bb.half_padding = padding // 2
+    bb.kind, bb.num_stack, bb.stack_size, bb.kernel_size = "mdtc", num_stack, stack_size, k
+    return bb
+
+
+def _tcn(num_layers: int, ch: int, k: int, dropout: float, ds: bool) -> nn.Module:
+    """network.{i}.cnn.{0,1[,3,4]} with dilation 2**i (tcn.py:75-84, 101-114, 133-137)."""
+    net = nn.ModuleList()
+    padding = 0
+    for i in range(num_layers):
+        d = 2 ** i
+        if ds:
+            cnn = nn.Sequential(nn.Conv1d(ch, ch, k, dilation=d, groups=ch), nn.BatchNorm1d(ch), nn.ReLU(),
+                                nn.Conv1d(ch, ch, 1), nn.BatchNorm1d(ch), nn.ReLU(), nn.Dropout(dropout))
+        else:
+            cnn = nn.Sequential(nn.Conv1d(ch, ch, k, dilation=d), nn.BatchNorm1d(ch), nn.ReLU(),
+                                nn.Dropout(dropout))
+        blk = _holder(cnn=cnn)
+        blk.padding = (k - 1) * d
+        padding += blk.padding
+        net.append(blk)
+    bb = _holder(network=net)
+    bb.padding = padding
+    bb.kind, bb.num_layers, bb.kernel_size, bb.ds = ("ds_tcn" if ds else "tcn"), num_layers, k, ds
+    return bb
+
+
+def _linear_classifier(idim: int, odim: int) -> nn.Module:
+    """state_dict: linear.{weight,bias} (classifier.py:57-61)."""
+    return _holder(linear=nn.Linear(idim, odim))
+
+
+class KWSModel(nn.Module):
+    """wekws/model/kws_model.py:33-95, executed by libwekws_b200.so."""
+
+    def __init__(self, idim: int, odim: int, hdim: int, global_cmvn: Optional[nn.Module],
+                 preprocessing: Optional[nn.Module], backbone: nn.Module, classifier: nn.Module,
+                 activation: nn.Module):
+        super().__init__()
+        self.idim, self.odim, self.hdim = idim, odim, hdim
+        self.global_cmvn = global_cmvn
+        self.preprocessing = preprocessing
+        self.backbone = backbone
+        self.classifier = classifier
+        self.activation = activation
+        self._handle = None          # wekws_model*
+        self._handle_dev = None
+        self._dirty = True
+
+    # ---------------------------------------------------------------- weight life-cycle
+    def invalidate(self) -> None:
+        """Call after editing parameters in place by hand; load_state_dict/.to() do it themselves."""
+        self._dirty = True
+
+    def load_state_dict(self, *args, **kwargs):
+        self._dirty = True
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._dirty = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def _release(self) -> None:
+        if self._handle is not None:
+            try:
+                _native.lib().wekws_model_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    def __getstate__(self):      # the native handle is rebuilt lazily after copy / unpickle
+        state = self.__dict__.copy()
+        state["_handle"], state["_handle_dev"], state["_dirty"] = None, None, True
+        return state
+
+    def _native_config(self) -> _native.ModelConfig:
+        bb = self.backbone
+        cfg = _native.ModelConfig()
+        cfg.idim, cfg.hdim, cfg.odim = self.idim, self.hdim, self.odim
+        if isinstance(bb, nn.GRU):
+            if not (bb.batch_first and not bb.bidirectional and bb.bias and bb.input_size == bb.hidden_size):
+                raise NotImplementedError("wekws_b200: only GRU(hdim, hdim, batch_first=True) is supported")
+            cfg.backbone, cfg.num_layers, cfg.hdim = _native.BACKBONE_GRU, bb.num_layers, bb.hidden_size
+        elif getattr(bb, "kind", None) == "mdtc":
+            cfg.backbone = _native.BACKBONE_MDTC
+            cfg.num_stack, cfg.stack_size, cfg.kernel_size = bb.num_stack, bb.stack_size, bb.kernel_size
+        elif getattr(bb, "kind", None) in ("tcn", "ds_tcn"):
+            cfg.backbone = _native.BACKBONE_DSTCN if bb.ds else _native.BACKBONE_TCN
+            cfg.num_layers, cfg.kernel_size = bb.num_layers, bb.kernel_size
+        else:
+            raise NotImplementedError(f"wekws_b200: backbone {type(bb).__name__} has no fused kernel")
+        if isinstance(self.activation, nn.Sigmoid):
+            cfg.activation = _native.ACT_SIGMOID
+        elif isinstance(self.activation, nn.Identity):
+            cfg.activation = _native.ACT_IDENTITY
+        else:
+            raise NotImplementedError("wekws_b200: activation must be nn.Sigmoid or nn.Identity")
+        cfg.norm_var = 1 if (self.global_cmvn is None or self.global_cmvn.norm_var) else 0
+        return cfg
+
+    def _build_handle(self, finalize: bool = True):
+        """Creates the native model and feeds it the state_dict by its reference key names."""
+        lib = _native.lib()
+        self._release()
+        cfg = self._native_config()
+        h = C.c_void_p()
+        _native.check(lib.wekws_model_create(C.byref(cfg), C.byref(h)), "wekws_model_create")
+        self._handle = h
+        for name, t in self.state_dict().items():
+            if name.endswith("num_batches_tracked"):
+                continue
+            host = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            _native.check(lib.wekws_model_set_tensor(h, name.encode(), C.c_void_p(host.data_ptr()), host.numel()),
+                          f"wekws_model_set_tensor({name})")
+        if finalize:
+            _native.check(lib.wekws_model_finalize(h), "wekws_model_finalize")
+        else:
+            _native.check(lib.wekws_model_pack(h), "wekws_model_pack")
+        return h
+
+    def _ensure(self, device: torch.device):
+        if self._dirty or self._handle is None or self._handle_dev != device:
+            with torch.cuda.device(device):
+                self._build_handle(finalize=True)
+            self._handle_dev = device
+            self._dirty = False
+        return self._handle
+
+    # ------------------------------------------------------------------------- forward
+    def _run(self, x: torch.Tensor, in_cache: torch.Tensor, flags: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.training:
+            raise RuntimeError("wekws_b200.KWSModel is inference-only: call model.eval() first "
+                               "(training-mode BatchNorm/Dropout are not implemented)")
+        if not x.is_cuda:
+            raise RuntimeError("wekws_b200.KWSModel runs on CUDA (sm_100a) only; got a CPU tensor. "
+                               "There is no CPU fallback -- move the model and inputs to a B200.")
+        if x.dtype != torch.float32:
+            raise TypeError(f"wekws_b200.KWSModel expects float32 features, got {x.dtype}")
+        if x.dim() != 3 or x.size(2) != self.idim:
+            raise ValueError(f"features must be (B, T, {self.idim}), got {tuple(x.shape)}")
+        dev = x.device
+        B, T = x.size(0), x.size(1)
+        x = x.contiguous()
+        gru = isinstance(self.backbone, nn.GRU)
+        cache_shape = (self.backbone.num_layers, B, self.hdim) if gru else (B, self.hdim, self.backbone.padding)
+        cache_ptr = None
+        if in_cache is not None and in_cache.numel() > 0:
+            if tuple(in_cache.shape) != cache_shape:
+                raise ValueError(f"in_cache must be {cache_shape}, got {tuple(in_cache.shape)}")
+            in_cache = in_cache.to(device=dev, dtype=torch.float32).contiguous()
+            cache_ptr = C.c_void_p(in_cache.data_ptr())
+        h = self._ensure(dev)
+        out = torch.empty(B, T, self.odim, device=dev, dtype=torch.float32)
+        if T == 0 and cache_ptr is not None:
+            out_cache = in_cache.clone()
+        elif T == 0:
+            out_cache = torch.zeros(cache_shape, device=dev, dtype=torch.float32)
+        else:
+            out_cache = torch.empty(cache_shape, device=dev, dtype=torch.float32)
+        if B > 0 and T > 0:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = _native.lib().wekws_model_forward(
+                    h, C.c_void_p(x.data_ptr()), cache_ptr, C.c_void_p(out.data_ptr()),
+                    C.c_void_p(out_cache.data_ptr()), B, T, flags, C.c_void_p(stream))
+            _native.check(rc, "wekws_model_forward")
+        return out, out_cache
+
+    def forward(self, x: torch.Tensor, in_cache: torch.Tensor = _EMPTY) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run(x, in_cache, 0)
+
+    def forward_softmax(self, x: torch.Tensor, in_cache: torch.Tensor = _EMPTY) -> Tuple[torch.Tensor, torch.Tensor]:
+        """kws_model.py:78-90 -- softmax over the output dim after the activation."""
+        return self._run(x, in_cache, _native.FWD_SOFTMAX)
+
+    def fuse_modules(self):
+        """The reference fuses conv+bn+relu for int8 PTQ (static_quantize.py:94); here every
+        BatchNorm is already folded natively at pack time, so there is nothing to do."""
+        return None
+
+
+def init_model(configs: dict) -> KWSModel:
+    """Config -> model factory with the reference's keys and defaults (kws_model.py:97-214)."""
+    cmvn = configs.get("cmvn", {})
+    if "cmvn_file" in cmvn and cmvn["cmvn_file"] is not None:
+        loader = load_kaldi_cmvn if "kaldi" in cmvn["cmvn_file"] else load_cmvn
+        mean, istd = loader(cmvn["cmvn_file"])
+        global_cmvn = GlobalCMVN(torch.from_numpy(mean).float(), torch.from_numpy(istd).float(), cmvn["norm_var"])
+    else:
+        global_cmvn = None
+
+    input_dim, output_dim, hidden_dim = configs["input_dim"], configs["output_dim"], configs["hidden_dim"]
+
+    prep_type = configs["preprocessing"]["type"]
+    if prep_type == "linear":
+        preprocessing = _linear_subsampling(input_dim, hidden_dim)
+    elif prep_type in ("cnn1d_s1", "none"):
+        raise NotImplementedError(f"wekws_b200: preprocessing type '{prep_type}' is outside the fused hot path "
+                                  "(SURVEY.md section 2 row 4); only 'linear' is implemented")
+    else:
+        print("Unknown preprocessing type {}".format(prep_type))
+        sys.exit(1)
+
+    bb = configs["backbone"]
+    if bb["type"] == "gru":
+        backbone = nn.GRU(hidden_dim, hidden_dim, num_layers=bb["num_layers"], batch_first=True)
+    elif bb["type"] == "tcn":
+        backbone = _tcn(bb["num_layers"], hidden_dim, bb.get("kernel_size", 8), bb.get("dropout", 0.1),
+                        bb.get("ds", False))
+    elif bb["type"] == "mdtc":
+        hidden_dim = bb["hidden_dim"]
+        assert bb["causal"] is True, "we now only support causal mdtc"
+        backbone = _mdtc(bb["num_stack"], bb["stack_size"], hidden_dim, bb["kernel_size"])
+    elif bb["type"] == "fsmn":
+        raise NotImplementedError("wekws_b200: the FSMN backbone is outside the fused hot path "
+                                  "(SURVEY.md section 8f row f4)")
+    else:
+        print("Unknown body type {}".format(bb["type"]))
+        sys.exit(1)
+
+    if "classifier" in configs:
+        raise NotImplementedError("wekws_b200: the speech-command 'classifier' heads (global/last) are "
+                                  "outside the streaming hot path (SURVEY.md section 2 row 8)")
+    classifier = _linear_classifier(hidden_dim, output_dim)
+    activation: nn.Module = nn.Sigmoid()
+    if "activation" in configs:
+        if configs["activation"]["type"] == "identity":
+            activation = nn.Identity()
+        else:
+            print("Unknown activation type {}".format(configs["activation"]["type"]))
+            sys.exit(1)
+    return KWSModel(input_dim, output_dim, hidden_dim, global_cmvn, preprocessing, backbone, classifier,
+                    activation)
