@@ -47,14 +47,14 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by every BN in mdtc.py / tcn
 
 
 # --------------------------------------------------------------------------- Fbank
-def povey_window(n: int) -> Tensor:
-    """kaldi.py:98-100: hann(n, periodic=False) ** 0.85 in fp32."""
-    return torch.hann_window(n, periodic=False, dtype=torch.float32).pow(0.85)
+def povey_window(n: int, dtype=torch.float32) -> Tensor:
+    """kaldi.py:98-100: hann(n, periodic=False) ** 0.85 (fp32 in the reference)."""
+    return torch.hann_window(n, periodic=False, dtype=dtype).pow(0.85)
 
 
-def hamming_window(n: int) -> Tensor:
+def hamming_window(n: int, dtype=torch.float32) -> Tensor:
     """kaldi.py:96-97 / runtime/core/frontend/fbank.h:90-96."""
-    return torch.hamming_window(n, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32)
+    return torch.hamming_window(n, periodic=False, alpha=0.54, beta=0.46, dtype=dtype)
 
 
 def mel_scale(f: Tensor) -> Tensor:
@@ -62,7 +62,7 @@ def mel_scale(f: Tensor) -> Tensor:
 
 
 def mel_banks(num_bins: int, n_fft: int, sample_rate: float,
-              low_freq: float = 20.0, high_freq: float = 0.0) -> Tensor:
+              low_freq: float = 20.0, high_freq: float = 0.0, dtype=torch.float32) -> Tensor:
     """kaldi.py:436-511 with vtln_warp == 1.0.  Returns (num_bins, n_fft//2 + 1);
     the extra last column (Nyquist) is the zero pad of kaldi.py:627."""
     num_fft_bins = n_fft // 2
@@ -77,10 +77,10 @@ def mel_banks(num_bins: int, n_fft: int, sample_rate: float,
     left = mel_low + b * delta
     center = mel_low + (b + 1.0) * delta
     right = mel_low + (b + 2.0) * delta
-    mel = mel_scale(fft_bin_width * torch.arange(num_fft_bins, dtype=torch.float32)).unsqueeze(0)
+    mel = mel_scale(fft_bin_width * torch.arange(num_fft_bins, dtype=dtype)).unsqueeze(0)
     up = (mel - left) / (center - left)
     down = (right - mel) / (right - center)
-    bins = torch.max(torch.zeros(1), torch.min(up, down))
+    bins = torch.max(torch.zeros(1, dtype=dtype), torch.min(up, down))
     return F.pad(bins, (0, 1), mode="constant", value=0.0)
 
 
@@ -93,11 +93,12 @@ def num_frames(num_samples: int, frame_len: int = 400, frame_shift: int = 160) -
 
 def fbank(waveform: Tensor, num_mel_bins: int = 80, frame_length: float = 25.0,
           frame_shift: float = 10.0, sample_frequency: float = 16000.0,
-          window_type: str = "povey", preemphasis: float = 0.97) -> Tensor:
+          window_type: str = "povey", preemphasis: float = 0.97, dtype=torch.float32) -> Tensor:
     """Kaldi log-mel filterbank of one waveform (N,) in int16-scale floats, with
     the arguments the reference passes (dither=0, energy_floor=0, rest default).
-    Returns (m, num_mel_bins)."""
-    wav = waveform.to(torch.float32).reshape(-1)
+    Returns (m, num_mel_bins).  dtype=float64 evaluates the same formulas in double
+    (the 'exact arithmetic' yardstick tests use to rank fp32 implementations)."""
+    wav = waveform.to(dtype).reshape(-1)
     win = int(sample_frequency * frame_length * 0.001)
     shift = int(sample_frequency * frame_shift * 0.001)
     n_fft = 1 if win == 0 else 2 ** (win - 1).bit_length()
@@ -108,13 +109,13 @@ def fbank(waveform: Tensor, num_mel_bins: int = 80, frame_length: float = 25.0,
     frames = frames - frames.mean(dim=1, keepdim=True)                    # :183-186
     prev = F.pad(frames.unsqueeze(0), (1, 0), mode="replicate").squeeze(0)[:, :-1]
     frames = frames - preemphasis * prev                                  # :193-198
-    w = povey_window(win) if window_type == "povey" else hamming_window(win)
+    w = povey_window(win, dtype) if window_type == "povey" else hamming_window(win, dtype)
     frames = frames * w.unsqueeze(0)                                      # :201-204
     frames = F.pad(frames, (0, n_fft - win))                              # :207-211
     spec = torch.fft.rfft(frames).abs().pow(2.0)                          # :616-618
-    mel = mel_banks(num_mel_bins, n_fft, sample_frequency)                # :621-627
+    mel = mel_banks(num_mel_bins, n_fft, sample_frequency, dtype=dtype)   # :621-627
     e = torch.mm(spec, mel.T)                                             # :630
-    return torch.max(e, torch.tensor(EPS)).log()                          # :633
+    return torch.max(e, torch.tensor(EPS, dtype=dtype)).log()             # :633
 
 
 # ---------------------------------------------------------------------------- CMVN
