@@ -137,6 +137,12 @@ WEKWS_API int wekws_model_set_tensor(wekws_model* m, const char* name, const flo
 WEKWS_API int wekws_model_pack(wekws_model* m);
 /* wekws_model_pack + upload to the current device.                                       */
 WEKWS_API int wekws_model_finalize(wekws_model* m);
+/* Arithmetic of the dense GEMMs: 0 = auto (default): tcgen05 tensor cores with a 3-pass bf16
+ * operand split (~2^-17 relative, posteriors within 1e-5 of fp32) where a fused tensor-core
+ * kernel exists (mdtc, hidden 64, chunk >= 8 frames), FP32 FMA elsewhere; 1 = FP32 FMA only. */
+WEKWS_API int wekws_model_set_precision(wekws_model* m, int mode);
+/* 1 if a forward with T frames per call runs the tcgen05 kernel (after finalize), else 0.    */
+WEKWS_API int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T);
 /* Debug/test accessors of the packed host-side program (valid after finalize).      */
 WEKWS_API int64_t wekws_model_packed_floats(const wekws_model* m, int which /*0 stream, 1 vectors*/);
 WEKWS_API int wekws_model_packed_copy(const wekws_model* m, int which, float* h_dst, int64_t capacity);

@@ -221,3 +221,27 @@ def test_launch_counter_counts_our_kernels(native, models):
     m(x)
     Fbank(80)(torch.zeros(1, 16000, device=DEV))
     assert native.launch_count() == n0 + 2
+
+
+@pytest.mark.parametrize("case", ["mdtc", "mdtc_cmvn_logits"])
+def test_tensor_core_and_fp32_paths_agree(case, models):
+    """mdtc/hidden-64 runs on tcgen05 (bf16x3) by default; the FP32-FMA kernel is the exact path."""
+    cfg, m, sd, _ = models(case)
+    B, T = 37, 40
+    x = synth.features(B, T, 80, seed=5, cmvn_like=m.global_cmvn is not None).to(DEV)
+    cache = torch.randn(B, 64, 244, generator=torch.Generator().manual_seed(3)).to(DEV)
+    try:
+        m.precision = "fp32"
+        y32, c32 = m(x, cache)
+        assert not m.uses_tensor_cores(T)
+        m.precision = "auto"
+        ytc, ctc = m(x, cache)
+        assert m.uses_tensor_cores(T) and not m.uses_tensor_cores(4)
+    finally:
+        m.precision = "auto"
+    assert torch.equal(c32[:, :, :4], ctc[:, :, :4])            # first cache slice is a pure copy of x
+    assert (ytc - y32).abs().max() <= 0.5 * _tol(y32.cpu().numpy())
+    assert (ctc - c32).abs().max() <= 0.5 * _tol(c32.cpu().numpy())
+    y_ref, c_ref = O.kws_forward(sd, cfg, x.cpu(), cache.cpu())
+    assert (ytc.cpu() - y_ref).abs().max() <= _tol(y_ref.numpy())
+    assert (y32.cpu() - y_ref).abs().max() <= 0.2 * _tol(y_ref.numpy())

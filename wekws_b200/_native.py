@@ -49,6 +49,8 @@ SIGNATURES = {
     "wekws_model_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "wekws_model_pack": (C.c_int, [C.c_void_p]),
     "wekws_model_finalize": (C.c_int, [C.c_void_p]),
+    "wekws_model_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "wekws_model_uses_tensor_cores": (C.c_int, [C.c_void_p, C.c_int64]),
     "wekws_model_packed_floats": (C.c_int64, [C.c_void_p, C.c_int]),
     "wekws_model_packed_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "wekws_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

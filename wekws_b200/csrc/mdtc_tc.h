@@ -1,0 +1,31 @@
+// Kernel argument block of the tensor-core MDTC kernel (mdtc_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_backbone.h"
+
+namespace wekws {
+
+struct TcArgs {
+  const float* feats;      // (B, T, idim), stream stride feat_bstride
+  const float* in_cache;   // (B, 64, P) or nullptr
+  float* out;              // (B, T, odim), stream stride out_bstride
+  float* out_cache;        // (B, 64, P)
+  const uint8_t* wimg;     // pre-swizzled bf16 hi|lo weight images, 16 KB per slot:
+                           //   [Wp atom0][Wp atom1][blk0 W1][blk0 W2][blk1 W1]...
+  const float* vec;        // same per-channel vector blob as the FFMA kernel
+  int B, T;
+  long long feat_bstride, out_bstride;
+  int idim, odim, nblocks, ktaps, P, stack_size, act, has_cmvn;
+  int v_mean, v_istd, v_bp, v_blocks, v_blk_stride, v_wc, v_bc;
+  int dil[kMaxBlocks];
+  int coff[kMaxBlocks];
+  int smax;                // streams per tile (set by mdtc_tc_launch)
+};
+
+bool tc_eligible(const TcArgs& a, int padmax);
+int tc_max_T();
+int mdtc_tc_launch(TcArgs a, int padmax, cudaStream_t st);
+
+}  // namespace wekws

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "conv_backbone.h"
 #include "gru.h"
+#include "mdtc_tc.h"
 
 namespace wekws {
 
@@ -85,6 +86,13 @@ struct wekws_model {
   ConvArgs conv{};
   GruArgs gru{};
   int conv_max_T = 0;
+  // tensor-core path (mdtc, hidden 64)
+  std::vector<std::vector<float>> folded;   // folded GEMM weights W^T [K][64] in consumption order
+  std::vector<uint8_t> h_wimg;
+  uint8_t* d_wimg = nullptr;
+  bool tc_ok = false;
+  int precision = 0;                        // 0 auto (tensor cores where eligible), 1 fp32 FFMA only
+  TcArgs tcargs{};
 };
 
 namespace {
@@ -126,6 +134,10 @@ size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
 // Appends W^T (K x C, from W[o][c] * s[o] with arbitrary source strides) as row chunks.
 void push_gemm(wekws_model* m, int K, int C, const float* W, size_t o_stride, size_t c_stride, const double* s) {
   const int KC = conv_chunk_rows(C);
+  m->folded.emplace_back((size_t)K * C);
+  for (int k = 0; k < K; ++k)
+    for (int o = 0; o < C; ++o)
+      m->folded.back()[(size_t)k * C + o] = (float)((double)W[o * o_stride + k * c_stride] * (s ? s[o] : 1.0));
   for (int k0 = 0; k0 < K; k0 += KC) {
     const int kk = K - k0 < KC ? K - k0 : KC;
     m->h_chunk_off.push_back((int)m->h_stream.size());
@@ -167,6 +179,60 @@ int pack_classifier(wekws_model* m, int H, int* v_wc, int* v_bc) {
   return WEKWS_OK;
 }
 
+
+// round-to-nearest-even fp32 -> bf16 (as __floats2bfloat162_rn does on the device)
+uint16_t bf16_rn(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);      // inf / nan
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float bf16_to_f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// K-major SWIZZLE_128B image of W[n][k0 .. k0+64) (n < 64): hi at dst, lo at dst + 8192 (tc_common.cuh)
+void write_w_image(uint8_t* dst, const std::vector<float>& wt /*[K][64]*/, int K, int k0) {
+  memset(dst, 0, 16384);
+  for (int n = 0; n < 64; ++n)
+    for (int kk = 0; kk < 64 && k0 + kk < K; ++kk) {
+      const float w = wt[(size_t)(k0 + kk) * 64 + n];
+      const uint16_t hi = bf16_rn(w);
+      const uint16_t lo = bf16_rn(w - bf16_to_f(hi));
+      const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+      memcpy(dst + off, &hi, 2);
+      memcpy(dst + 8192 + off, &lo, 2);
+    }
+}
+
+// Tensor-core eligibility + pre-swizzled bf16x3 weight images (mdtc_tc.cu)
+void pack_tc(wekws_model* m) {
+  m->tc_ok = false;
+  m->h_wimg.clear();
+  const wekws_model_config& c = m->cfg;
+  if (c.backbone != WEKWS_BACKBONE_MDTC || c.hdim != 64) return;
+  TcArgs& t = m->tcargs;
+  memset(&t, 0, sizeof(t));
+  const ConvArgs& a = m->conv;
+  t.idim = a.idim; t.odim = a.odim; t.nblocks = a.nblocks; t.ktaps = a.ktaps; t.P = a.P;
+  t.stack_size = a.stack_size; t.act = a.act; t.has_cmvn = a.has_cmvn;
+  t.v_mean = a.v_mean; t.v_istd = a.v_istd; t.v_bp = a.v_bp; t.v_blocks = a.v_blocks;
+  t.v_blk_stride = a.v_blk_stride; t.v_wc = a.v_wc; t.v_bc = a.v_bc;
+  for (int b = 0; b < a.nblocks; ++b) { t.dil[b] = a.dil[b]; t.coff[b] = a.coff[b]; }
+  if (!tc_eligible(t, m->padmax)) return;
+  if (m->folded.size() != (size_t)(1 + 2 * a.nblocks)) return;
+  m->h_wimg.assign((size_t)(2 + 2 * a.nblocks) * 16384, 0);
+  write_w_image(m->h_wimg.data(), m->folded[0], a.idim, 0);
+  if (a.idim > 64) write_w_image(m->h_wimg.data() + 16384, m->folded[0], a.idim, 64);
+  for (int g = 0; g < 2 * a.nblocks; ++g)
+    write_w_image(m->h_wimg.data() + (size_t)(2 + g) * 16384, m->folded[1 + g], 64, 0);
+  m->tc_ok = true;
+}
+
 int pack_conv(wekws_model* m) {
   const wekws_model_config& c = m->cfg;
   const int C = c.hdim, K = c.kernel_size, idim = c.idim;
@@ -200,7 +266,7 @@ int pack_conv(wekws_model* m) {
     m->padding += pad;
     if (pad > m->padmax) m->padmax = pad;
   }
-  m->h_stream.clear(); m->h_vec.clear(); m->h_chunk_off.clear();
+  m->h_stream.clear(); m->h_vec.clear(); m->h_chunk_off.clear(); m->folded.clear();
   ConvArgs& a = m->conv;
   memset(&a, 0, sizeof(a));
   int rc = pack_common_front(m, &a.v_mean, &a.v_istd);
@@ -265,6 +331,7 @@ int pack_conv(wekws_model* m) {
   a.has_cmvn = m->has_cmvn ? 1 : 0;
   a.n_chunks = (int)m->h_chunk_off.size() - 1;
   for (int b = 0; b < m->nblocks; ++b) { a.dil[b] = m->dil[b]; a.coff[b] = m->coff[b]; }
+  pack_tc(m);
   return WEKWS_OK;
 }
 
@@ -308,8 +375,8 @@ int pack_gru(wekws_model* m) {
 }
 
 void free_device(wekws_model* m) {
-  cudaFree(m->d_stream); cudaFree(m->d_vec); cudaFree(m->d_chunk_off);
-  m->d_stream = nullptr; m->d_vec = nullptr; m->d_chunk_off = nullptr;
+  cudaFree(m->d_stream); cudaFree(m->d_vec); cudaFree(m->d_chunk_off); cudaFree(m->d_wimg);
+  m->d_stream = nullptr; m->d_vec = nullptr; m->d_chunk_off = nullptr; m->d_wimg = nullptr;
 }
 
 }  // namespace
@@ -380,6 +447,11 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
     WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_chunk_off, m->h_chunk_off.size() * sizeof(int)));
     WEKWS_CUDA_OK(cudaMemcpy(m->d_chunk_off, m->h_chunk_off.data(), m->h_chunk_off.size() * sizeof(int), cudaMemcpyHostToDevice));
     m->conv.wstream = m->d_stream; m->conv.chunk_off = m->d_chunk_off; m->conv.vec = m->d_vec;
+    if (m->tc_ok) {
+      WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_wimg, m->h_wimg.size()));
+      WEKWS_CUDA_OK(cudaMemcpy(m->d_wimg, m->h_wimg.data(), m->h_wimg.size(), cudaMemcpyHostToDevice));
+      m->tcargs.wimg = m->d_wimg; m->tcargs.vec = m->d_vec;
+    }
     m->conv_max_T = conv_backbone_max_T(m->conv, m->padmax);
     WEKWS_REQUIRE(m->conv_max_T >= 1, "model does not fit the fused kernel's shared memory");
   } else {
@@ -387,6 +459,16 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
   }
   m->finalized = true;
   return WEKWS_OK;
+}
+
+extern "C" int wekws_model_set_precision(wekws_model* m, int mode) {
+  WEKWS_REQUIRE(m && (mode == 0 || mode == 1), "wekws_model_set_precision: mode must be 0 (auto) or 1 (fp32)");
+  m->precision = mode;
+  return WEKWS_OK;
+}
+
+extern "C" int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T) {
+  return (m && m->finalized && m->tc_ok && m->precision == 0 && T >= 8) ? 1 : 0;
 }
 
 extern "C" int64_t wekws_model_packed_floats(const wekws_model* m, int which) {
@@ -423,10 +505,28 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
   } else {
     // time-chunk long inputs; the cache carries the state between chunks exactly as in
     // streaming use (chunked == full utterance, SURVEY.md 8a "Numerical facts")
-    const int maxT = m->conv_max_T;
+    // tensor-core path: mdtc hidden 64, chunks of >= 8 frames, 16-byte aligned cache rows
+    const bool use_tc = m->tc_ok && m->precision == 0 && T >= 8 &&
+                        (d_in_cache == nullptr || ((uintptr_t)d_in_cache & 15) == 0) &&
+                        ((uintptr_t)d_feats & 15) == 0;
+    const int maxT = use_tc ? tc_max_T() : m->conv_max_T;
     const int nchunk = (int)((T + maxT - 1) / maxT);
     const int Tc = (int)((T + nchunk - 1) / nchunk);
     for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+      if (use_tc) {
+        TcArgs a = m->tcargs;
+        a.feats = d_feats + t0 * m->cfg.idim;
+        a.out = d_out + t0 * m->cfg.odim;
+        a.in_cache = t0 == 0 ? d_in_cache : d_out_cache;
+        a.out_cache = d_out_cache;
+        a.B = (int)B;
+        a.T = (int)(T - t0 < Tc ? T - t0 : Tc);
+        a.feat_bstride = T * m->cfg.idim;
+        a.out_bstride = T * m->cfg.odim;
+        int rc = mdtc_tc_launch(a, m->padmax, st);
+        if (rc) return rc;
+        continue;
+      }
       ConvArgs a = m->conv;
       a.feats = d_feats + t0 * m->cfg.idim;
       a.out = d_out + t0 * m->cfg.odim;

@@ -1,0 +1,151 @@
+// sm_100a building blocks for the tensor-core path: mbarrier, bulk async copies (TMA engine),
+// tcgen05 MMA / TMEM alloc / TMEM load, UMMA shared-memory + instruction descriptors, and the
+// bf16 "x3" operand split (x ~ b0 + b1, products b0*w0 + b1*w0 + b0*w1, ~2^-17 relative error).
+//
+// Operand layout used everywhere here: K-major, SWIZZLE_128B, bf16.  A row of a 64-wide K slab
+// is 128 bytes = 8 chunks of 16 B; chunk j of row r lives at position j ^ (r & 7); rows are
+// packed 8 x 128 B = 1024 B per core-matrix group (SBO = 1024), so an [R][64] bf16 operand is a
+// dense R*128-byte image whose base must be 1024-byte aligned.  One tcgen05.mma consumes K = 16
+// (32 bytes of every row): the K step advances the descriptor start address by 32 bytes.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wekws {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ------------------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// -------------------------------------------------------------------- bulk async copies
+// global -> shared, completion signalled on an mbarrier as transaction bytes (16 B granularity)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------- tcgen05
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {         // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all tcgen05 ops issued so far by this thread arrive on `bar` when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA instruction descriptor: bf16 A/B (K-major), fp32 accumulate, M x N  (cute mma_sm100_desc.hpp:412-434)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4)                       // c_format  = F32
+         | (1u << 7)                     // a_format  = BF16
+         | (1u << 10)                    // b_format  = BF16
+         | ((uint32_t)(N >> 3) << 17)    // n_dim
+         | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+// UMMA shared-memory descriptor, K-major SWIZZLE_128B (cute mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, 16-byte units   [0,14)
+  d |= (uint64_t)1 << 16;                                // leading byte offset (unused)   [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset = 1024 B    [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)    [46,48)
+  d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B       [61,64)
+  return d;
+}
+// advance a K-major SW128 descriptor by `ksteps` MMA K-steps (16 bf16 = 32 bytes each)
+__device__ __forceinline__ uint64_t sdesc_advance_k(uint64_t desc, int ksteps) { return desc + (uint64_t)(ksteps * 2); }
+
+// byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a K-major SW128 operand image
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// ------------------------------------------------------------------------- bf16 x3 split
+// x ~ b0 + b1 with b0 = bf16(x), b1 = bf16(x - b0); two values packed per 32-bit word (lo = first)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float r0 = x0 - __low2float(h), r1 = x1 - __high2float(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// splits 8 consecutive K values and stores them as one 16-byte chunk into each operand image
+__device__ __forceinline__ void split_store8(const float (&v)[8], uint8_t* img_hi, uint8_t* img_lo, uint32_t off) {
+  uint4 h, l;
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+  *reinterpret_cast<uint4*>(img_hi + off) = h;
+  *reinterpret_cast<uint4*>(img_lo + off) = l;
+}
+
+}  // namespace tc
+}  // namespace wekws

@@ -125,6 +125,10 @@ class KWSModel(nn.Module):
         self._handle = None          # wekws_model*
         self._handle_dev = None
         self._dirty = True
+        # "auto": tcgen05 tensor cores (3-pass bf16 split, ~1e-5 of fp32) where a fused kernel exists,
+        # FP32 FMA elsewhere; "fp32": FP32 FMA kernels only.
+        self.precision = "auto"
+        self._precision_applied = None
 
     # ---------------------------------------------------------------- weight life-cycle
     def invalidate(self) -> None:
@@ -140,12 +144,13 @@ class KWSModel(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     def _release(self) -> None:
-        if self._handle is not None:
+        h = self.__dict__.get("_handle")
+        if h is not None:
             try:
-                _native.lib().wekws_model_destroy(self._handle)
+                _native.lib().wekws_model_destroy(h)
             except Exception:
                 pass
-            self._handle = None
+            self.__dict__["_handle"] = None
 
     def __del__(self):
         self._release()
@@ -153,6 +158,7 @@ class KWSModel(nn.Module):
     def __getstate__(self):      # the native handle is rebuilt lazily after copy / unpickle
         state = self.__dict__.copy()
         state["_handle"], state["_handle_dev"], state["_dirty"] = None, None, True
+        state["_precision_applied"] = None
         return state
 
     def _native_config(self) -> _native.ModelConfig:
@@ -206,7 +212,15 @@ class KWSModel(nn.Module):
                 self._build_handle(finalize=True)
             self._handle_dev = device
             self._dirty = False
+            self._precision_applied = None
         return self._handle
+
+    def uses_tensor_cores(self, T: int) -> bool:
+        '''True if a forward with T frames per call takes the tcgen05 kernel (model already on a GPU).'''
+        if self._handle is None or self._dirty:
+            return False
+        return bool(_native.lib().wekws_model_uses_tensor_cores(self._handle, T)) and self.precision == "auto"
+
 
     # ------------------------------------------------------------------------- forward
     def _run(self, x: torch.Tensor, in_cache: torch.Tensor, flags: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -232,6 +246,12 @@ class KWSModel(nn.Module):
             in_cache = in_cache.to(device=dev, dtype=torch.float32).contiguous()
             cache_ptr = C.c_void_p(in_cache.data_ptr())
         h = self._ensure(dev)
+        if self._precision_applied != self.precision:
+            if self.precision not in ("auto", "fp32"):
+                raise ValueError("precision must be 'auto' or 'fp32'")
+            _native.check(_native.lib().wekws_model_set_precision(h, 0 if self.precision == "auto" else 1),
+                          "wekws_model_set_precision")
+            self._precision_applied = self.precision
         out = torch.empty(B, T, self.odim, device=dev, dtype=torch.float32)
         if T == 0 and cache_ptr is not None:
             out_cache = in_cache.clone()
