@@ -9,18 +9,22 @@
 //   * weights arrive as pre-swizzled 16 KB images by cp.async.bulk (TMA engine) into a 2-slot ring,
 //     cache slices arrive as per-(stream,channel) bulk copies -- all signalled on mbarriers.
 //
-// One CTA per SM: 16 compute warps + 1 producer warp that owns every asynchronous engine (bulk copies,
-// MMA issue).  TWO row tiles (<=128 frames each) are in flight.  There is no CTA-wide barrier in the
-// steady state: compute warps hand finished operand tiles to the producer through mbarriers
-// (a_rdy[t], 512 arrivals) and keep going; the producer issues the tile's MMAs, which complete on
-// mma_bar[t]; compute warps block only when they actually need an accumulator:
+// One CTA per SM: 16 compute warps, one MMA-issue warp (also streams the weights) and one loader
+// warp (cache slices by 2-D TMA tensor copies: one instruction per stream and block).  TWO row tiles
+// (<=128 frames each) are in flight.  There is no CTA-wide barrier in the steady state: compute warps
+// hand finished operand tiles over through mbarriers (a_rdy[t], one arrival per warp) and keep going;
+// the issue warp launches the tile's MMAs, which complete on mma_bar[t]; compute warps block only when
+// they actually need an accumulator:
 //
 //   compute : DW(0) DW(1) EPI1(0) EPI1(1) EPI2(0) EPI2(1) |bar| DW(0) ...      (per block)
-//   producer:      MMA1(0) MMA1(1)  MMA2(0)  MMA2(1)   + next block's cache slices and weights
+//   issuer  :      MMA1(0) MMA1(1)  MMA2(0)  MMA2(1)   + next block's weights
+//   loader  :      slice(0,blk+1) slice(1,blk+1)
 //
 // Everywhere a lane owns a ROW (frame) of the tile: the depthwise conv reads the time-minor residual
 // stream X[c][col] (cache slice and frames of a stream contiguous) conflict-free and writes whole
 // 16-byte operand chunks (8 channels of its row); epilogues own the TMEM lane of their row.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mdtc_tc.h"
 #include "tc_common.cuh"
@@ -33,33 +37,49 @@ using namespace tc;
 
 constexpr int NCW = 16;                    // compute warps
 constexpr int NCT = NCW * 32;              // compute threads
-constexpr int NT_TC = NCT + 32;            // + producer / MMA-issue warp
+constexpr int NT_TC = NCT + 64;            // + MMA-issue warp (NCW) + loader warp (NCW + 1)
 constexpr int C = 64;
 // X[t] holds, per channel c, the streams of the tile back to back in "cat" form
-//     X[c][s * Lw + (PADR - pad) .. s * Lw + PADR)   cache slice of the current block (bulk-copied in)
+//     X[c][s * Lw + (PADR - pad) .. s * Lw + PADR)   cache slice of the current block (copied in by the loader)
 //     X[c][s * Lw + PADR .. + T)                     the residual stream x of stream s
 // (Lw = PADR + roundup4(T), PADR = roundup4(max pad)) so cat(cache, x) is simply contiguous columns.
-constexpr int RPX = 232;                   // row stride (floats): S * Lw <= XCOLS, + 4 spare (dummy) columns
-constexpr int XCOLS = 228;                 // usable columns; column XCOLS is the write target of padding rows
+constexpr int RPX = 160;                   // row stride (floats)
+constexpr int XCOLS = 156;                 // usable columns (S * Lw <= XCOLS); column XCOLS absorbs padding rows
 constexpr int A_BYTES = 128 * 128;         // one [128][64] bf16 operand image
-constexpr int X_BYTES = 64 * RPX * 4;      // 59392 (multiple of 1024; also hosts the 2 atom-1 images)
+constexpr int X_BYTES = 64 * RPX * 4;      // 40960 (multiple of 1024; also hosts the 2 atom-1 images)
+constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
+constexpr int NSLOT = 6;                   // landing slots: NSLOT - 1 slices in flight hide the HBM latency
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
 constexpr int OFF_A = 0;                                   // 2 tiles x (hi, lo)
 constexpr int OFF_X = OFF_A + 2 * 2 * A_BYTES;             // 65536
-constexpr int OFF_W = OFF_X + 2 * X_BYTES;                 // 184320
-constexpr int SMEM_TOTAL = OFF_W + 2 * W_SLOT + 1024;      // + alignment slack = 218112
+constexpr int OFF_STG = OFF_X + 2 * X_BYTES;               // 147456
+constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 196608
+constexpr int SMEM_TOTAL = OFF_W + 2 * W_SLOT + 1024;      // + alignment slack = 230400
 static_assert(X_BYTES % 1024 == 0 && X_BYTES >= 2 * A_BYTES, "X region must host two operand images");
+static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+// 2-D TMA tensor copy global -> shared (box given by the tensor map), completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
 
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 
-__global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  __shared__ uint64_t mma_bar[2], halo_bar[2], w_bar[2], a_rdy[2], w_free[2];
+  __shared__ uint64_t mma_bar[2], halo_bar[2], w_bar[2], a_rdy[2], w_free[2], h_free[2], stg_bar[NSLOT];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_prod = warp == NCW;
+  const bool is_prod = warp == NCW, is_loader = warp == NCW + 1;
   const int q = warp & 3, g = (warp >> 2) & 3;    // TMEM lane quarter / 16-column group of this warp
   const int row = 32 * q + lane;                  // epilogue row of this thread
   const int T = a.T, K = a.ktaps;
@@ -68,13 +88,15 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
   uint8_t* Ahi[2] = {base + OFF_A, base + OFF_A + 2 * A_BYTES};
   uint8_t* Alo[2] = {Ahi[0] + A_BYTES, Ahi[1] + A_BYTES};
   float* X[2] = {reinterpret_cast<float*>(base + OFF_X), reinterpret_cast<float*>(base + OFF_X + X_BYTES)};
+  float* STG = reinterpret_cast<float*>(base + OFF_STG);      // NSLOT landing slots of STG_FLOATS
   uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 1); mbar_init(&w_bar[i], 1);
-      mbar_init(&a_rdy[i], NCT); mbar_init(&w_free[i], 1);
+      mbar_init(&a_rdy[i], NCW); mbar_init(&w_free[i], 1); mbar_init(&h_free[i], NCW);
     }
+    for (int i = 0; i < NSLOT; ++i) mbar_init(&stg_bar[i], 1);
     mbar_fence_init();
   }
   if (is_prod) tmem_alloc(&tmem_slot, 128);
@@ -84,9 +106,11 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
   const uint32_t tmem = tmem_slot;
   // phase parities (every waiter keeps its own copy; all copies advance in lock step)
   uint32_t mma_par[2] = {0, 0}, halo_par[2] = {0, 0}, w_par[2] = {0, 0}, ar_par[2] = {0, 0}, wf_par[2] = {0, 0};
+  uint32_t hf_par[2] = {0, 0}, lm_par[2] = {0, 0};
+  uint32_t jobctr = 0;                           // loader: landing-slot use counter (slot = ctr % NSLOT)
+  const int PADR = a.padr, Lw = a.padr + ((T + 3) & ~3);
   const uint32_t idesc = make_idesc_bf16(128, 64);
   const int natoms = (a.idim + 63) / 64;
-  const int PADR = a.padr, Lw = a.padr + ((T + 3) & ~3);
 
   // balanced contiguous partition of the streams over the grid
   const int sb = (int)(((long long)a.B * blockIdx.x) / gridDim.x);
@@ -105,108 +129,138 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
     done += take;
 
     if (is_prod) {
-      // ================================================================== PRODUCER WARP
-      auto issue_halo = [&](int t, int blk) {       // cache slice of block blk -> pad columns in front of each stream
-        if (S[t] == 0) return;
-        const int pad = a.dil[blk] * (K - 1), off = a.coff[blk];
-        const int nrow = S[t] * C;
-        if (a.in_cache != nullptr) {
-          if (lane == 0) mbar_arrive_expect_tx(&halo_bar[t], (uint32_t)(nrow * pad * 4));
-          __syncwarp();
-          for (int r = lane; r < nrow; r += 32) {
-            const int s = r >> 6, c = r & 63;
-            bulk_g2s(X[t] + c * RPX + s * Lw + PADR - pad, a.in_cache + ((size_t)(b0[t] + s) * C + c) * a.P + off,
-                     (uint32_t)(pad * 4), &halo_bar[t]);
-          }
-        } else {
-          for (int r = lane; r < nrow; r += 32) {
-            float* dst = X[t] + (r & 63) * RPX + (r >> 6) * Lw + PADR - pad;
-            for (int p = 0; p < pad; ++p) dst[p] = 0.f;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&halo_bar[t]);
-        }
-      };
-      auto load_w = [&](int slot, const uint8_t* src) {       // lane 0 only
-        mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
-        bulk_g2s(Wslot[slot], src, W_SLOT, &w_bar[slot]);
-      };
-      // 3-pass bf16x3 GEMM of tile t: D (+)= A * W^T over `ksteps` K-steps of one operand atom
-      auto issue_gemm = [&](int t, const uint8_t* ahi, const uint8_t* alo, const uint8_t* wimg, int ksteps,
-                            uint32_t& acc) {
-        const uint64_t da_hi = make_sdesc_sw128(smem_u32(ahi)), da_lo = make_sdesc_sw128(smem_u32(alo));
-        const uint64_t dw_hi = make_sdesc_sw128(smem_u32(wimg)), dw_lo = make_sdesc_sw128(smem_u32(wimg + 8192));
-        const uint32_t d = tmem + 64 * t;
-        for (int k = 0; k < ksteps; ++k) { umma_bf16(d, sdesc_advance_k(da_hi, k), sdesc_advance_k(dw_hi, k), idesc, acc); acc = 1; }
-        for (int k = 0; k < ksteps; ++k) umma_bf16(d, sdesc_advance_k(da_lo, k), sdesc_advance_k(dw_hi, k), idesc, 1);
-        for (int k = 0; k < ksteps; ++k) umma_bf16(d, sdesc_advance_k(da_hi, k), sdesc_advance_k(dw_lo, k), idesc, 1);
-      };
-      auto wait_a = [&](int t) {                     // lane 0: operand images of tile t complete
-        mbar_wait(&a_rdy[t], ar_par[t]);
-        tc_fence_after();
-      };
-      const int ks0 = (min(a.idim, 64) + 15) >> 4, ks1 = natoms > 1 ? (a.idim - 64 + 15) >> 4 : 0;
-
-      // ---- first Linear
+      // ================================================================== MMA-ISSUE WARP (lane 0 works)
       if (lane == 0) {
+        auto load_w = [&](int slot, const uint8_t* src) {
+          mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
+          bulk_g2s(Wslot[slot], src, W_SLOT, &w_bar[slot]);
+        };
+        // 3-pass bf16x3 GEMM of tile t: D (+)= A * W^T over `ksteps` K-steps of one operand atom
+        auto issue_gemm = [&](int t, uint64_t da_hi, uint64_t da_lo, uint64_t dw_hi, uint64_t dw_lo, int ksteps,
+                              uint32_t& acc) {
+          const uint32_t d = tmem + 64 * t;
+          for (int k = 0; k < ksteps; ++k) { umma_bf16(d, da_hi + 2 * k, dw_hi + 2 * k, idesc, acc); acc = 1; }
+          for (int k = 0; k < ksteps; ++k) umma_bf16(d, da_lo + 2 * k, dw_hi + 2 * k, idesc, 1);
+          for (int k = 0; k < ksteps; ++k) umma_bf16(d, da_hi + 2 * k, dw_lo + 2 * k, idesc, 1);
+        };
+        auto wait_a = [&](int t) {                   // operand images of tile t complete
+          mbar_wait(&a_rdy[t], ar_par[t]);
+          ar_par[t] ^= 1;
+          tc_fence_after();
+        };
+        uint64_t dA_hi[2], dA_lo[2], dX_hi[2], dX_lo[2], dW_hi[2], dW_lo[2];
+        for (int i = 0; i < 2; ++i) {
+          dA_hi[i] = make_sdesc_sw128(smem_u32(Ahi[i])); dA_lo[i] = make_sdesc_sw128(smem_u32(Alo[i]));
+          dX_hi[i] = make_sdesc_sw128(smem_u32(X[i])); dX_lo[i] = make_sdesc_sw128(smem_u32(X[i]) + A_BYTES);
+          dW_hi[i] = make_sdesc_sw128(smem_u32(Wslot[i])); dW_lo[i] = make_sdesc_sw128(smem_u32(Wslot[i]) + 8192);
+        }
+        const int ks0 = (min(a.idim, 64) + 15) >> 4, ks1 = natoms > 1 ? (a.idim - 64 + 15) >> 4 : 0;
+
+        // ---- first Linear
         load_w(0, a.wimg);
         if (natoms > 1) load_w(1, a.wimg + W_SLOT);
-        mbar_wait(&w_bar[0], w_par[0]);
-        if (natoms > 1) mbar_wait(&w_bar[1], w_par[1]);
+        mbar_wait(&w_bar[0], w_par[0]); w_par[0] ^= 1;
+        if (natoms > 1) { mbar_wait(&w_bar[1], w_par[1]); w_par[1] ^= 1; }
         for (int t = 0; t < 2; ++t) {
           if (S[t] == 0) continue;
           wait_a(t);
           uint32_t acc = 0;
-          issue_gemm(t, Ahi[t], Alo[t], Wslot[0], ks0, acc);
-          if (natoms > 1)
-            issue_gemm(t, reinterpret_cast<uint8_t*>(X[t]), reinterpret_cast<uint8_t*>(X[t]) + A_BYTES, Wslot[1], ks1, acc);
+          issue_gemm(t, dA_hi[t], dA_lo[t], dW_hi[0], dW_lo[0], ks0, acc);
+          if (natoms > 1) issue_gemm(t, dX_hi[t], dX_lo[t], dW_hi[1], dW_lo[1], ks1, acc);
           umma_commit(&mma_bar[t]);
         }
         umma_commit(&w_free[0]);
-        // the X regions double as atom-1 operand images and both weight slots are busy until these GEMMs finish
-        mbar_wait(&w_free[0], wf_par[0]);
+        // both weight slots are busy until these GEMMs finish
+        mbar_wait(&w_free[0], wf_par[0]); wf_par[0] ^= 1;
         load_w(0, a.wimg + 2 * W_SLOT);
         load_w(1, a.wimg + 3 * W_SLOT);
-      }
-      w_par[0] ^= 1;
-      if (natoms > 1) w_par[1] ^= 1;
-      wf_par[0] ^= 1;
-      if (S[0]) ar_par[0] ^= 1;
-      if (S[1]) ar_par[1] ^= 1;
-      __syncwarp();
-      issue_halo(0, 0);
-      issue_halo(1, 0);
 
-      // ---- blocks
-      for (int blk = 0; blk < a.nblocks; ++blk) {
-        const bool more = blk + 1 < a.nblocks;
-        const uint8_t* wnext = a.wimg + (size_t)(2 + 2 * (blk + 1)) * W_SLOT;
-        for (int phase = 0; phase < 2; ++phase) {          // phase 0: pointwise-1 GEMMs, phase 1: conv2 GEMMs
-          if (lane == 0) mbar_wait(&w_bar[phase], w_par[phase]);
-          w_par[phase] ^= 1;
-          for (int t = 0; t < 2; ++t) {
-            if (S[t] == 0) continue;
-            if (lane == 0) {
+        // ---- blocks
+        for (int blk = 0; blk < a.nblocks; ++blk) {
+          const bool more = blk + 1 < a.nblocks;
+          const uint8_t* wnext = a.wimg + (size_t)(2 + 2 * (blk + 1)) * W_SLOT;
+          for (int phase = 0; phase < 2; ++phase) {        // phase 0: pointwise-1 GEMMs, phase 1: conv2 GEMMs
+            mbar_wait(&w_bar[phase], w_par[phase]); w_par[phase] ^= 1;
+            for (int t = 0; t < 2; ++t) {
+              if (S[t] == 0) continue;
               wait_a(t);
               uint32_t acc = 0;
-              issue_gemm(t, Ahi[t], Alo[t], Wslot[phase], 4, acc);
-              umma_commit(&mma_bar[t]);
+              if (a.debug & 1) { mbar_arrive(&mma_bar[t]); }
+              else { issue_gemm(t, dA_hi[t], dA_lo[t], dW_hi[phase], dW_lo[phase], 4, acc); umma_commit(&mma_bar[t]); }
             }
-            ar_par[t] ^= 1;
-            __syncwarp();
-            // DW(t) of this block is complete once its operand tile was handed over: its cache columns are free
-            if (phase == 0 && more) issue_halo(t, blk + 1);
+            umma_commit(&w_free[phase]);
+            if (phase == 1) {      // slot 0 drained long ago: refill it while the conv2 GEMMs run
+              mbar_wait(&w_free[0], wf_par[0]); wf_par[0] ^= 1;
+              if (more) load_w(0, wnext);
+            }
           }
-          if (lane == 0) umma_commit(&w_free[phase]);
+          mbar_wait(&w_free[1], wf_par[1]); wf_par[1] ^= 1;
+          if (more) load_w(1, wnext + W_SLOT);
         }
-        // refill the weight ring (these waits return as soon as the GEMMs above have drained)
-        for (int phase = 0; phase < 2; ++phase) {
+      }
+    } else if (is_loader) {
+      // ================================================================== LOADER WARP
+      // cache slice of (block, tile, stream): one 2-D TMA copy [64][pad] into a landing slot, then the warp
+      // scatters it into the pad columns in front of the stream's frames in X[t] (conflict-free float4 copies)
+      const int njobs = a.nblocks * take;            // jobs ordered by (blk, tile, stream)
+      auto job_of = [&](int k, int& blk, int& t, int& s) {
+        blk = k / take;
+        const int r = k - blk * take;
+        t = r >= S[0] ? 1 : 0;
+        s = t ? r - S[0] : r;
+      };
+      auto issue_tma = [&](int k) {                  // lane 0
+        int blk, t, s;
+        job_of(k, blk, t, s);
+        const int pad = a.dil[blk] * (K - 1);
+        const uint32_t slot = (jobctr + (uint32_t)k) % NSLOT;
+        mbar_arrive_expect_tx(&stg_bar[slot], (uint32_t)(C * pad * 4));
+        tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0[t] + s) * C, &stg_bar[slot]);
+      };
+      const bool have_cache = a.in_cache != nullptr;
+      if (have_cache && lane == 0)
+        for (int k = 0; k < NSLOT - 1 && k < njobs; ++k) issue_tma(k);
+      for (int k = 0; k < njobs; ++k) {
+        int blk, t, s;
+        job_of(k, blk, t, s);
+        const int pad = a.dil[blk] * (K - 1);
+        // the slot of job k + NSLOT - 1 is the one job k - 1 used: drained (program order + fence below)
+        if (have_cache && lane == 0 && k + NSLOT - 1 < njobs) issue_tma(k + NSLOT - 1);
+        if (s == 0) {                                // first stream of this (block, tile): X[t]'s pad columns free?
           if (lane == 0) {
-            mbar_wait(&w_free[phase], wf_par[phase]);
-            if (more) load_w(phase, wnext + phase * W_SLOT);
+            if (blk == 0) mbar_wait(&mma_bar[t], lm_par[t]);              // first-Linear GEMM no longer reads X[t]
+            else mbar_wait(&h_free[t], hf_par[t]);                        // DW(t, blk-1) done
           }
-          wf_par[phase] ^= 1;
+          if (blk == 0) lm_par[t] ^= 1; else hf_par[t] ^= 1;              // (mma_bar: odd number of phases per iteration)
         }
+        float* dst0 = X[t] + s * Lw + PADR - pad;
+        const int v4 = pad >> 2, n4 = C * v4;
+        if (have_cache) {
+          const uint32_t use = jobctr + (uint32_t)k, slot = use % NSLOT;
+          if (lane == 0) mbar_wait(&stg_bar[slot], (use / NSLOT) & 1);
+          __syncwarp();
+          const float4* src = reinterpret_cast<const float4*>(STG + slot * STG_FLOATS);
+          for (int i = lane; i < n4; i += 32) {
+            const int c = i / v4, v = i - c * v4;
+            *reinterpret_cast<float4*>(dst0 + c * RPX + 4 * v) = src[i];
+          }
+        } else {
+          __syncwarp();
+          for (int i = lane; i < n4; i += 32) {
+            const int c = i / v4, v = i - c * v4;
+            *reinterpret_cast<float4*>(dst0 + c * RPX + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        fence_proxy_async();                         // landing slot was read through the generic proxy; TMA rewrites it
+        __syncwarp();
+        if (s == S[t] - 1 && lane == 0) mbar_arrive(&halo_bar[t]);       // whole tile's slice is in place
+      }
+      if (have_cache) jobctr += (uint32_t)njobs;
+      // DW of the last block still signals h_free: consume it so the parities stay in step
+      for (int t = 0; t < 2; ++t) {
+        if (S[t] == 0) continue;
+        if (lane == 0) mbar_wait(&h_free[t], hf_par[t]);
+        hf_par[t] ^= 1;
       }
     } else {
       // ================================================================== COMPUTE WARPS
@@ -221,10 +275,11 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
         const int cx = rb == 0 ? colx[0] : rb == 1 ? colx[1] : rb == 2 ? colx[2] : colx[3];
         return (rb * 32 + lane < rows[t]) ? cx : XCOLS;
       };
-      auto hand_over = [&](int t) {                  // operand images of tile t written -> producer may issue
+      auto hand_over = [&](int t) {                  // this warp's part of tile t's operand images is written
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(&a_rdy[t]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_rdy[t]);
       };
       auto wait_mma = [&](int t) {
         mbar_wait(&mma_bar[t], mma_par[t]);
@@ -298,29 +353,42 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
         // (row block, channel group) tasks; the warp order is mirrored for tile 1 so both tiles together balance
         const int nrb = (rows[t] + 31) >> 5;
         const int w = t ? NCW - 1 - warp : warp;
-        for (int task = w; task < nrb * 8; task += NCW) {
+        const uint32_t xs = smem_u32(X[t]);
+        for (int task = w; task < ((a.debug & 2) ? 0 : nrb * 8); task += NCW) {
           const int rb = task >> 3, cg = task & 7;
-          const int c0 = col_of(rb, t) - pad;
+          // tap j of channel c reads X[c][col - pad + j*d]: per tap one base address, channels at immediate offsets
+          const uint32_t base = xs + 4u * (uint32_t)(cg * 8 * RPX + col_of(rb, t) - pad);
+          const float4* wv = reinterpret_cast<const float4*>(vb + cg * 8);
           float v[8];
+          {
+            const float4 ba = __ldg(wv + (K * C) / 4), bb = __ldg(wv + (K * C) / 4 + 1);
+            v[0] = ba.x; v[1] = ba.y; v[2] = ba.z; v[3] = ba.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+          }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = cg * 8 + i;
-            const float* x0 = X[t] + c * RPX + c0;
-            float acc = __ldg(vb + K * C + c);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < K) acc = fmaf(__ldg(vb + j * C + c), x0[j * d], acc);
-            v[i] = acc;
+          for (int j = 0; j < 8; ++j) {
+            if (j < K) {
+              const float4 wa = __ldg(wv + (j * C) / 4), wb = __ldg(wv + (j * C) / 4 + 1);
+              const uint32_t aj = base + 4u * (uint32_t)(j * d);
+              v[0] = fmaf(wa.x, lds_f32(aj + 0 * RPX * 4), v[0]);
+              v[1] = fmaf(wa.y, lds_f32(aj + 1 * RPX * 4), v[1]);
+              v[2] = fmaf(wa.z, lds_f32(aj + 2 * RPX * 4), v[2]);
+              v[3] = fmaf(wa.w, lds_f32(aj + 3 * RPX * 4), v[3]);
+              v[4] = fmaf(wb.x, lds_f32(aj + 4 * RPX * 4), v[4]);
+              v[5] = fmaf(wb.y, lds_f32(aj + 5 * RPX * 4), v[5]);
+              v[6] = fmaf(wb.z, lds_f32(aj + 6 * RPX * 4), v[6]);
+              v[7] = fmaf(wb.w, lds_f32(aj + 7 * RPX * 4), v[7]);
+            }
           }
           split_store8(v, Ahi[t], Alo[t], sw128_offset(rb * 32 + lane, cg));
         }
         hand_over(t);
+        if (lane == 0) mbar_arrive(&h_free[t]);      // (after the __syncwarp in hand_over) cache columns consumed
       };
       // h = relu(D + b1) -> operand images A[t]                             (mdtc.py:115)
       auto epi1 = [&](int t, int blk) {
         const float* b1 = vec + a.v_blocks + blk * a.v_blk_stride + (K + 1) * C + 16 * g;
         wait_mma(t);
-        if (32 * q < rows[t]) {
+        if (32 * q < rows[t] && !(a.debug & 4)) {
           float d[16];
           tmem_ld16(tm_lane + 64 * t, d);
 #pragma unroll
@@ -342,7 +410,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const TcArgs a) {
         const float* b2 = vec + a.v_blocks + blk * a.v_blk_stride + (K + 2) * C + 16 * g;
         const bool stack_end = (blk > 0) && (blk % a.stack_size == 0);
         wait_mma(t);
-        if (32 * q >= rows[t]) return;
+        if (32 * q >= rows[t] || (a.debug & 4)) return;
         float d[16];
         tmem_ld16(tm_lane + 64 * t, d);
         float* xp = X[t] + (16 * g) * RPX + col_of(q, t);
@@ -427,18 +495,63 @@ bool tc_eligible(const TcArgs& a, int padmax) {
   return true;
 }
 
-int tc_max_T() { return 128; }
+int tc_max_T() { return 120; }
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+}  // namespace
 
 int mdtc_tc_launch(TcArgs a, int padmax, cudaStream_t st) {
-  WEKWS_REQUIRE(a.T >= 1 && a.T <= 128 && a.B >= 1, "mdtc_tc_launch: bad shape");
+  WEKWS_REQUIRE(a.T >= 1 && a.T <= 120 && a.B >= 1, "mdtc_tc_launch: bad shape");
   a.padr = (padmax + 3) & ~3;
-  a.pad_pow2 = 1;
-  while (a.pad_pow2 < padmax) a.pad_pow2 <<= 1;
   const int Lw = a.padr + ((a.T + 3) & ~3);
   int smax = 128 / a.T;
   if (smax > XCOLS / Lw) smax = XCOLS / Lw;
   WEKWS_REQUIRE(smax >= 1, "mdtc_tc_launch: tile does not fit");
   a.smax = smax;
+  {
+    const char* dbg = getenv("WEKWS_TC_DEBUG");    // timing experiments only (results are wrong when set)
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
+  // tensor maps over the incoming cache (B*64 rows of P floats): one per distinct slice width
+  if (a.in_cache != nullptr) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    WEKWS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    int pads[4], npads = 0;
+    for (int b = 0; b < a.nblocks; ++b) {
+      const int pad = a.dil[b] * (a.ktaps - 1);
+      int i = 0;
+      while (i < npads && pads[i] != pad) ++i;
+      if (i == npads) {
+        WEKWS_REQUIRE(npads < 4, "more than 4 distinct cache slice widths");
+        pads[npads++] = pad;
+        const cuuint64_t gdim[2] = {(cuuint64_t)a.P, (cuuint64_t)a.B * C};
+        const cuuint64_t gstr[1] = {(cuuint64_t)a.P * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)pad, (cuuint32_t)C};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult rc = enc(&a.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.in_cache), gdim,
+                                gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        WEKWS_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+      }
+      a.tmap_idx[b] = i;
+    }
+  }
   const int sms = device_sm_count();
   const int grid = a.B < sms ? a.B : sms;
   static bool attr_set[64] = {false};

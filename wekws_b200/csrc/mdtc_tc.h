@@ -1,5 +1,6 @@
 // Kernel argument block of the tensor-core MDTC kernel (mdtc_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,7 +22,10 @@ struct TcArgs {
   int v_mean, v_istd, v_bp, v_blocks, v_blk_stride, v_wc, v_bc;
   int dil[kMaxBlocks];
   int coff[kMaxBlocks];
-  int smax, padr, pad_pow2;  // streams per tile, roundup4(max pad), pow2 >= max pad (set by mdtc_tc_launch)
+  int debug;               // WEKWS_TC_DEBUG timing-experiment flags (0 in normal use)
+  int smax, padr;          // streams per tile, roundup4(max pad) (set by mdtc_tc_launch)
+  int tmap_idx[kMaxBlocks];               // block -> tensor map (one per distinct pad)
+  alignas(64) CUtensorMap tmap[4];        // 2-D maps over in_cache viewed as [B*64][P], box [64][pad]
 };
 
 bool tc_eligible(const TcArgs& a, int padmax);
