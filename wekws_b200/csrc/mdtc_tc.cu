@@ -37,7 +37,7 @@ using namespace tc;
 
 constexpr int NCW = 16;                    // compute warps
 constexpr int NCT = NCW * 32;              // compute threads
-constexpr int NT_TC = NCT + 64;            // + MMA-issue warp (NCW) + loader warp (NCW + 1)
+constexpr int NT_TC = NCT + 96;            // + MMA-issue warp (NCW) + one loader warp per tile (NCW+1, NCW+2)
 constexpr int C = 64;
 // X[t] holds, per channel c, the streams of the tile back to back in "cat" form
 //     X[c][s * Lw + (PADR - pad) .. s * Lw + PADR)   cache slice of the current block (copied in by the loader)
@@ -48,13 +48,15 @@ constexpr int XCOLS = 156;                 // usable columns (S * Lw <= XCOLS); 
 constexpr int A_BYTES = 128 * 128;         // one [128][64] bf16 operand image
 constexpr int X_BYTES = 64 * RPX * 4;      // 40960 (multiple of 1024; also hosts the 2 atom-1 images)
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
-constexpr int NSLOT = 6;                   // landing slots: NSLOT - 1 slices in flight hide the HBM latency
+constexpr int NSLOT = 4;                   // landing slots: 2 per tile (one block of slices in flight per tile)
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
 constexpr int OFF_A = 0;                                   // 2 tiles x (hi, lo)
 constexpr int OFF_X = OFF_A + 2 * 2 * A_BYTES;             // 65536
 constexpr int OFF_STG = OFF_X + 2 * X_BYTES;               // 147456
-constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 196608
-constexpr int SMEM_TOTAL = OFF_W + 2 * W_SLOT + 1024;      // + alignment slack = 230400
+constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 188416
+constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 221184: per-block vectors (taps, biases), 2 x 2 KB
+constexpr int VEC_FLOATS = 512;                            // (K + 3) * 64 floats, K <= 5
+constexpr int SMEM_TOTAL = OFF_VEC + 2 * VEC_FLOATS * 4 + 1024;   // + alignment slack = 226304
 static_assert(X_BYTES % 1024 == 0 && X_BYTES >= 2 * A_BYTES, "X region must host two operand images");
 static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
@@ -75,11 +77,11 @@ __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0
 __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  __shared__ uint64_t mma_bar[2], halo_bar[2], w_bar[2], a_rdy[2], w_free[2], h_free[2], stg_bar[NSLOT];
+  __shared__ uint64_t mma_bar[2], halo_bar[2], w_bar[2], a_rdy[2], w_free[2], h_free[2], stg_bar[NSLOT], vec_bar[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_prod = warp == NCW, is_loader = warp == NCW + 1;
+  const bool is_prod = warp == NCW, is_loader = warp > NCW;
   const int q = warp & 3, g = (warp >> 2) & 3;    // TMEM lane quarter / 16-column group of this warp
   const int row = 32 * q + lane;                  // epilogue row of this thread
   const int T = a.T, K = a.ktaps;
@@ -89,12 +91,15 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   uint8_t* Alo[2] = {Ahi[0] + A_BYTES, Ahi[1] + A_BYTES};
   float* X[2] = {reinterpret_cast<float*>(base + OFF_X), reinterpret_cast<float*>(base + OFF_X + X_BYTES)};
   float* STG = reinterpret_cast<float*>(base + OFF_STG);      // NSLOT landing slots of STG_FLOATS
+  float* VEC = reinterpret_cast<float*>(base + OFF_VEC);      // [2][VEC_FLOATS]
+  uint32_t sbase;                                             // shared-window address of `base`, pinned in a register
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(base)));
   uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 1); mbar_init(&w_bar[i], 1);
-      mbar_init(&a_rdy[i], NCW); mbar_init(&w_free[i], 1); mbar_init(&h_free[i], NCW);
+      mbar_init(&a_rdy[i], NCW); mbar_init(&w_free[i], 1); mbar_init(&h_free[i], NCW); mbar_init(&vec_bar[i], 1);
     }
     for (int i = 0; i < NSLOT; ++i) mbar_init(&stg_bar[i], 1);
     mbar_fence_init();
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   // phase parities (every waiter keeps its own copy; all copies advance in lock step)
   uint32_t mma_par[2] = {0, 0}, halo_par[2] = {0, 0}, w_par[2] = {0, 0}, ar_par[2] = {0, 0}, wf_par[2] = {0, 0};
   uint32_t hf_par[2] = {0, 0}, lm_par[2] = {0, 0};
+  uint32_t vec_par[2] = {0, 0};
   uint32_t jobctr = 0;                           // loader: landing-slot use counter (slot = ctr % NSLOT)
   const int PADR = a.padr, Lw = a.padr + ((T + 3) & ~3);
   const uint32_t idesc = make_idesc_bf16(128, 64);
@@ -143,8 +149,13 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           for (int k = 0; k < ksteps; ++k) umma_bf16(d, da_lo + 2 * k, dw_hi + 2 * k, idesc, 1);
           for (int k = 0; k < ksteps; ++k) umma_bf16(d, da_hi + 2 * k, dw_lo + 2 * k, idesc, 1);
         };
+        auto load_vec = [&](int blk) {               // taps + biases of block blk -> VEC[blk & 1]
+          mbar_arrive_expect_tx(&vec_bar[blk & 1], (uint32_t)(a.v_blk_stride * 4));
+          bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, vec + a.v_blocks + blk * a.v_blk_stride, (uint32_t)(a.v_blk_stride * 4),
+                   &vec_bar[blk & 1]);
+        };
         auto wait_a = [&](int t) {                   // operand images of tile t complete
-          mbar_wait(&a_rdy[t], ar_par[t]);
+          mbar_wait_backoff(&a_rdy[t], ar_par[t]);
           ar_par[t] ^= 1;
           tc_fence_after();
         };
@@ -157,6 +168,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         const int ks0 = (min(a.idim, 64) + 15) >> 4, ks1 = natoms > 1 ? (a.idim - 64 + 15) >> 4 : 0;
 
         // ---- first Linear
+        load_vec(0);                                 // VEC[0] was last read in the previous iteration (odd block count: by block nblocks-1 if even index)
         load_w(0, a.wimg);
         if (natoms > 1) load_w(1, a.wimg + W_SLOT);
         mbar_wait(&w_bar[0], w_par[0]); w_par[0] ^= 1;
@@ -196,70 +208,63 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           }
           mbar_wait(&w_free[1], wf_par[1]); wf_par[1] ^= 1;
           if (more) load_w(1, wnext + W_SLOT);
+          // VEC[(blk+1)&1] was last read by block blk-1, which every compute warp has left (they handed over EPI1 of blk)
+          if (more) load_vec(blk + 1);
         }
       }
     } else if (is_loader) {
-      // ================================================================== LOADER WARP
-      // cache slice of (block, tile, stream): one 2-D TMA copy [64][pad] into a landing slot, then the warp
-      // scatters it into the pad columns in front of the stream's frames in X[t] (conflict-free float4 copies)
-      const int njobs = a.nblocks * take;            // jobs ordered by (blk, tile, stream)
-      auto job_of = [&](int k, int& blk, int& t, int& s) {
-        blk = k / take;
-        const int r = k - blk * take;
-        t = r >= S[0] ? 1 : 0;
-        s = t ? r - S[0] : r;
-      };
-      auto issue_tma = [&](int k) {                  // lane 0
-        int blk, t, s;
-        job_of(k, blk, t, s);
-        const int pad = a.dil[blk] * (K - 1);
-        const uint32_t slot = (jobctr + (uint32_t)k) % NSLOT;
-        mbar_arrive_expect_tx(&stg_bar[slot], (uint32_t)(C * pad * 4));
-        tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0[t] + s) * C, &stg_bar[slot]);
-      };
-      const bool have_cache = a.in_cache != nullptr;
-      if (have_cache && lane == 0)
-        for (int k = 0; k < NSLOT - 1 && k < njobs; ++k) issue_tma(k);
-      for (int k = 0; k < njobs; ++k) {
-        int blk, t, s;
-        job_of(k, blk, t, s);
-        const int pad = a.dil[blk] * (K - 1);
-        // the slot of job k + NSLOT - 1 is the one job k - 1 used: drained (program order + fence below)
-        if (have_cache && lane == 0 && k + NSLOT - 1 < njobs) issue_tma(k + NSLOT - 1);
-        if (s == 0) {                                // first stream of this (block, tile): X[t]'s pad columns free?
-          if (lane == 0) {
-            if (blk == 0) mbar_wait(&mma_bar[t], lm_par[t]);              // first-Linear GEMM no longer reads X[t]
-            else mbar_wait(&h_free[t], hf_par[t]);                        // DW(t, blk-1) done
+      // ================================================================== LOADER WARPS (one per tile)
+      // cache slice of (block, stream) of this warp's tile: one 2-D TMA copy [64][pad] into a landing slot, then
+      // the warp scatters it into the pad columns in front of the stream's frames in X[t] (float4 copies)
+      const int t = warp - NCW - 1;
+      if (S[t] > 0) {
+        const int St = S[t], njobs = a.nblocks * St;   // jobs ordered by (blk, stream)
+        const bool have_cache = a.in_cache != nullptr;
+        auto issue_tma = [&](int k) {                  // lane 0
+          const int blk = k / St, sidx = k - blk * St;
+          const int pad = a.dil[blk] * (K - 1);
+          const uint32_t slot = 2 * t + ((jobctr + (uint32_t)k) & 1);
+          mbar_arrive_expect_tx(&stg_bar[slot], (uint32_t)(C * pad * 4));
+          tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0[t] + sidx) * C, &stg_bar[slot]);
+        };
+        if (have_cache && lane == 0) issue_tma(0);
+        for (int k = 0; k < njobs; ++k) {
+          const int blk = k / St, sidx = k - blk * St;
+          const int pad = a.dil[blk] * (K - 1);
+          // the slot of job k + 1 is the one job k - 1 used: drained (program order + proxy fence below)
+          if (have_cache && lane == 0 && k + 1 < njobs) issue_tma(k + 1);
+          if (sidx == 0) {                             // first stream of this block: are X[t]'s pad columns free?
+            if (lane == 0) {
+              if (blk == 0) mbar_wait_backoff(&mma_bar[t], lm_par[t]);    // first-Linear GEMM no longer reads X[t]
+              else mbar_wait_backoff(&h_free[t], hf_par[t]);              // DW(t, blk-1) done
+            }
+            if (blk == 0) lm_par[t] ^= 1; else hf_par[t] ^= 1;            // (mma_bar: odd number of phases per iteration)
           }
-          if (blk == 0) lm_par[t] ^= 1; else hf_par[t] ^= 1;              // (mma_bar: odd number of phases per iteration)
-        }
-        float* dst0 = X[t] + s * Lw + PADR - pad;
-        const int v4 = pad >> 2, n4 = C * v4;
-        if (have_cache) {
-          const uint32_t use = jobctr + (uint32_t)k, slot = use % NSLOT;
-          if (lane == 0) mbar_wait(&stg_bar[slot], (use / NSLOT) & 1);
+          // lane l copies float4 #(l + 32*it): channel c = c0 + it*cstep, float4 v of its pad/4
+          const int v4 = pad >> 2, cstep = 32 / v4, c0 = lane / v4, v = lane - c0 * v4, iters = 2 * v4;
+          float* dst = X[t] + sidx * Lw + PADR - pad + c0 * RPX + 4 * v;
+          const int dstep = cstep * RPX;
+          if (have_cache) {
+            const uint32_t use = jobctr + (uint32_t)k, slot = 2 * t + (use & 1);
+            if (lane == 0) mbar_wait_backoff(&stg_bar[slot], (use >> 1) & 1);
+            __syncwarp();
+            const float4* src = reinterpret_cast<const float4*>(STG + slot * STG_FLOATS) + lane;
+            for (int it = 0; it < iters; it += 2) {      // iters is even: two independent copies in flight
+              const float4 x0 = src[32 * it], x1 = src[32 * it + 32];
+              *reinterpret_cast<float4*>(dst + it * dstep) = x0;
+              *reinterpret_cast<float4*>(dst + (it + 1) * dstep) = x1;
+            }
+          } else {
+            __syncwarp();
+            for (int it = 0; it < iters; ++it) *reinterpret_cast<float4*>(dst + it * dstep) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          fence_proxy_async();                         // landing slot was read through the generic proxy; TMA rewrites it
           __syncwarp();
-          const float4* src = reinterpret_cast<const float4*>(STG + slot * STG_FLOATS);
-          for (int i = lane; i < n4; i += 32) {
-            const int c = i / v4, v = i - c * v4;
-            *reinterpret_cast<float4*>(dst0 + c * RPX + 4 * v) = src[i];
-          }
-        } else {
-          __syncwarp();
-          for (int i = lane; i < n4; i += 32) {
-            const int c = i / v4, v = i - c * v4;
-            *reinterpret_cast<float4*>(dst0 + c * RPX + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          if (sidx == St - 1 && lane == 0) mbar_arrive(&halo_bar[t]);     // whole tile's slice is in place
         }
-        fence_proxy_async();                         // landing slot was read through the generic proxy; TMA rewrites it
-        __syncwarp();
-        if (s == S[t] - 1 && lane == 0) mbar_arrive(&halo_bar[t]);       // whole tile's slice is in place
-      }
-      if (have_cache) jobctr += (uint32_t)njobs;
-      // DW of the last block still signals h_free: consume it so the parities stay in step
-      for (int t = 0; t < 2; ++t) {
-        if (S[t] == 0) continue;
-        if (lane == 0) mbar_wait(&h_free[t], hf_par[t]);
+        if (have_cache) jobctr += (uint32_t)njobs;
+        // DW of the last block still signals h_free: consume it so the parities stay in step
+        if (lane == 0) mbar_wait_backoff(&h_free[t], hf_par[t]);
         hf_par[t] ^= 1;
       }
     } else {
@@ -336,7 +341,11 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       // new cache slice + depthwise dilated conv (+folded BN) of block blk -> operand images A[t]
       auto dw = [&](int t, int blk) {
         const int d = a.dil[blk], pad = d * (K - 1), off = a.coff[blk];
-        const float* vb = vec + a.v_blocks + blk * a.v_blk_stride;
+        const float* vb = VEC + (blk & 1) * VEC_FLOATS;
+        if (t == 0) {                                // first use of this block's vectors
+          mbar_wait(&vec_bar[blk & 1], vec_par[blk & 1]);
+          vec_par[blk & 1] ^= 1;
+        }
         mbar_wait(&halo_bar[t], halo_par[t]);
         halo_par[t] ^= 1;
         {   // out_cache[b][c][off + j] = cat[c][T + j]                    (mdtc.py:113)
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         // (row block, channel group) tasks; the warp order is mirrored for tile 1 so both tiles together balance
         const int nrb = (rows[t] + 31) >> 5;
         const int w = t ? NCW - 1 - warp : warp;
-        const uint32_t xs = smem_u32(X[t]);
+        const uint32_t xs = sbase + OFF_X + t * X_BYTES;
         for (int task = w; task < ((a.debug & 2) ? 0 : nrb * 8); task += NCW) {
           const int rb = task >> 3, cg = task & 7;
           // tap j of channel c reads X[c][col - pad + j*d]: per tap one base address, channels at immediate offsets
@@ -361,13 +370,13 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           const float4* wv = reinterpret_cast<const float4*>(vb + cg * 8);
           float v[8];
           {
-            const float4 ba = __ldg(wv + (K * C) / 4), bb = __ldg(wv + (K * C) / 4 + 1);
+            const float4 ba = wv[(K * C) / 4], bb = wv[(K * C) / 4 + 1];
             v[0] = ba.x; v[1] = ba.y; v[2] = ba.z; v[3] = ba.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j < K) {
-              const float4 wa = __ldg(wv + (j * C) / 4), wb = __ldg(wv + (j * C) / 4 + 1);
+              const float4 wa = wv[(j * C) / 4], wb = wv[(j * C) / 4 + 1];
               const uint32_t aj = base + 4u * (uint32_t)(j * d);
               v[0] = fmaf(wa.x, lds_f32(aj + 0 * RPX * 4), v[0]);
               v[1] = fmaf(wa.y, lds_f32(aj + 1 * RPX * 4), v[1]);
@@ -386,15 +395,15 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       };
       // h = relu(D + b1) -> operand images A[t]                             (mdtc.py:115)
       auto epi1 = [&](int t, int blk) {
-        const float* b1 = vec + a.v_blocks + blk * a.v_blk_stride + (K + 1) * C + 16 * g;
+        const float* b1 = VEC + (blk & 1) * VEC_FLOATS + (K + 1) * C + 16 * g;
         wait_mma(t);
         if (32 * q < rows[t] && !(a.debug & 4)) {
           float d[16];
           tmem_ld16(tm_lane + 64 * t, d);
 #pragma unroll
           for (int hch = 0; hch < 2; ++hch) {
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(b1) + 2 * hch);
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(b1) + 2 * hch + 1);
+            const float4 ba = reinterpret_cast<const float4*>(b1)[2 * hch];
+            const float4 bb = reinterpret_cast<const float4*>(b1)[2 * hch + 1];
             float v[8];
             v[0] = fmaxf(d[hch * 8 + 0] + ba.x, 0.f); v[1] = fmaxf(d[hch * 8 + 1] + ba.y, 0.f);
             v[2] = fmaxf(d[hch * 8 + 2] + ba.z, 0.f); v[3] = fmaxf(d[hch * 8 + 3] + ba.w, 0.f);
@@ -407,7 +416,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       };
       // x' = relu(D + b2 + x) -> X[t]; multi-scale sum at the end of a stack  (mdtc.py:116-118, 266-273)
       auto epi2 = [&](int t, int blk, float (&ms)[16]) {
-        const float* b2 = vec + a.v_blocks + blk * a.v_blk_stride + (K + 2) * C + 16 * g;
+        const float* b2 = VEC + (blk & 1) * VEC_FLOATS + (K + 2) * C + 16 * g;
         const bool stack_end = (blk > 0) && (blk % a.stack_size == 0);
         wait_mma(t);
         if (32 * q >= rows[t] || (a.debug & 4)) return;
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         float* xp = X[t] + (16 * g) * RPX + col_of(q, t);
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(b2) + i4);
+          const float4 b = reinterpret_cast<const float4*>(b2)[i4];
           const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
 }  // namespace
 
 bool tc_eligible(const TcArgs& a, int padmax) {
-  if (a.idim % 8 != 0 || a.idim > 128 || a.odim > 8 || a.ktaps > 8) return false;
+  if (a.idim % 8 != 0 || a.idim > 128 || a.odim > 8 || a.ktaps > 5) return false;
   if (padmax > 32 || a.P % 4 != 0) return false;
   for (int b = 0; b < a.nblocks; ++b)
     if ((a.dil[b] * (a.ktaps - 1)) % 4 != 0 || a.coff[b] % 4 != 0) return false;
