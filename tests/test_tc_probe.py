@@ -29,3 +29,19 @@ def test_umma_bf16x3_gemm_matches_fp32(K):
     assert err <= 4e-5 * scale, (err, scale)          # bf16x3: ~2^-16 relative to sum |a||w|
     # and clearly better than a single bf16 pass (2^-8): proves all three passes accumulate
     assert err <= 1e-3 * scale
+
+
+def test_umma_a_operand_from_tmem():
+    """tcgen05.mma with the A operand in TMEM (written with tcgen05.st): rows = lanes, two bf16 per column."""
+    lib = C.CDLL(LIB)
+    lib.tc_probe_ts_run.restype = C.c_int
+    lib.tc_probe_ts_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    g = torch.Generator().manual_seed(7)
+    A = (torch.randn(128, 64, generator=g) * 3).cuda()
+    W = (torch.randn(64, 64, generator=g) * 0.3).cuda()
+    D = torch.full((128, 64), float("nan"), device="cuda")
+    assert lib.tc_probe_ts_run(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(D.data_ptr())) == 0
+    ref = (A.double() @ W.double().T)
+    err = (D.double() - ref).abs().max().item()
+    scale = (A.abs().double() @ W.abs().double().T).max().item()
+    assert err <= 4e-5 * scale, (err, scale)

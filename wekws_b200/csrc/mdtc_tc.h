@@ -23,7 +23,7 @@ struct TcArgs {
   int dil[kMaxBlocks];
   int coff[kMaxBlocks];
   int debug;               // WEKWS_TC_DEBUG timing-experiment flags (0 in normal use)
-  int smax, padr;          // streams per tile, roundup4(max pad) (set by mdtc_tc_launch)
+  int smax, spt, padr;     // streams per pass / per tile, roundup4(max pad) (set by mdtc_tc_launch)
   int tmap_idx[kMaxBlocks];               // block -> tensor map (one per distinct pad)
   alignas(64) CUtensorMap tmap[4];        // 2-D maps over in_cache viewed as [B*64][P], box [64][pad]
 };

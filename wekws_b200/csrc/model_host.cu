@@ -508,7 +508,7 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
     // tensor-core path: mdtc hidden 64, chunks of >= 8 frames, 16-byte aligned cache rows
     const bool use_tc = m->tc_ok && m->precision == 0 && T >= 8 &&
                         (d_in_cache == nullptr || ((uintptr_t)d_in_cache & 15) == 0) &&
-                        ((uintptr_t)d_feats & 15) == 0;
+                        ((uintptr_t)d_feats & 15) == 0 && ((uintptr_t)d_out_cache & 15) == 0;
     const int maxT = use_tc ? tc_max_T() : m->conv_max_T;
     const int nchunk = (int)((T + maxT - 1) / maxT);
     const int Tc = (int)((T + nchunk - 1) / nchunk);
