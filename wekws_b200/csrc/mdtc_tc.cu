@@ -43,14 +43,15 @@ constexpr int RPX = 512;                   // row stride (floats) of X[c][.]
 constexpr int XCOLS = 504;                 // usable columns (n_streams * Lw <= XCOLS); column XCOLS absorbs padding rows
 constexpr int X_BYTES = 64 * RPX * 4;      // 131072
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
-constexpr int NSLOT = 4;                   // 2 per loader warp
+constexpr int NSLOT = 7;                   // loader 0: slots 0..3, loader 1: slots 4..6 (depth 3 / 2 slices in flight)
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
 constexpr int VEC_FLOATS = 512;            // per-block vectors: (K + 3) * 64 floats, K <= 5
 constexpr int OFF_X = 0;
 constexpr int OFF_STG = OFF_X + X_BYTES;                   // 131072
-constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 163840
-constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 196608
-constexpr int SMEM_TOTAL = OFF_VEC + 2 * VEC_FLOATS * 4 + 1024;   // 201728 incl. alignment slack
+constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 188416
+constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 221184
+constexpr int SMEM_TOTAL = OFF_VEC + 2 * VEC_FLOATS * 4 + 1024;   // 226304 incl. alignment slack
+static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 // TMEM columns of tile i: [160 i, 160 i + 64) accumulator, + 64.. A hi (<= 48 cols), + 112.. A lo
 constexpr int TM_TILE = 160, TM_AHI = 64, TM_ALO = 112, TM_COLS = 512;
 
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dw_lo + 2 * k, idesc, 1);
         };
         auto wait_a = [&](int i) {                   // operand rows of tile i complete
-          mbar_wait_backoff(&a_rdy[i], (ar_par >> i) & 1);
+          mbar_wait(&a_rdy[i], (ar_par >> i) & 1);
           ar_par ^= 1u << i;
           tc_fence_after();
         };
@@ -211,15 +212,17 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       const int l = warp - NCW - 1;
       const int nmine = (ns - l + 1) / 2;              // my streams: l, l + 2, ...
       const int njobs = a.nblocks * nmine;
-      const bool have_cache = a.in_cache != nullptr;
+      const bool have_cache = a.in_cache != nullptr && !(a.debug & 16);
+      const int nsl = l == 0 ? 4 : 3, slot0 = l == 0 ? 0 : 4;   // my landing slots: a ring of nsl
       auto issue_tma = [&](int k) {                    // lane 0; job k = (blk, my m-th stream)
         const int blk = k / nmine, sg = l + 2 * (k - blk * nmine);
         const int pad = a.dil[blk] * (K - 1);
-        const uint32_t slot = 2 * l + ((jobctr + (uint32_t)k) & 1);
+        const uint32_t slot = slot0 + (jobctr + (uint32_t)k) % nsl;
         mbar_arrive_expect_tx(&stg_bar[slot], (uint32_t)(C * pad * 4));
         tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0 + sg) * C, &stg_bar[slot]);
       };
-      if (have_cache && lane == 0 && njobs > 0) issue_tma(0);
+      if (have_cache && lane == 0)
+        for (int k0 = 0; k0 < nsl - 1 && k0 < njobs; ++k0) issue_tma(k0);
       int k = 0;
       for (int blk = 0; blk < a.nblocks; ++blk) {
         const int pad = a.dil[blk] * (K - 1);
@@ -232,13 +235,13 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           }
           for (int sg = i * spt; sg < i * spt + tile_streams(i); ++sg) {
             if ((sg & 1) != l) continue;
-            if (have_cache && lane == 0 && k + 1 < njobs) issue_tma(k + 1);   // slot of job k-1: drained
-            const int v4 = pad >> 2, cstep = 32 / v4, c0 = lane / v4, v = lane - c0 * v4, iters = 2 * v4;
+            if (have_cache && lane == 0 && k + nsl - 1 < njobs) issue_tma(k + nsl - 1);   // reuses the slot of job k-1: drained
+            const int v4 = pad >> 2, sh = 31 - __clz(v4), cstep = 32 >> sh, c0 = lane >> sh, v = lane & (v4 - 1), iters = 2 * v4;
             float* dst = X + sg * Lw + PADR - pad + c0 * RPX + 4 * v;
             const int dstep = cstep * RPX;
             if (have_cache) {
-              const uint32_t use = jobctr + (uint32_t)k, slot = 2 * l + (use & 1);
-              if (lane == 0) mbar_wait_backoff(&stg_bar[slot], (use >> 1) & 1);
+              const uint32_t use = jobctr + (uint32_t)k, slot = slot0 + use % nsl;
+              if (lane == 0) mbar_wait_backoff(&stg_bar[slot], (use / nsl) & 1);
               __syncwarp();
               const float4* src = reinterpret_cast<const float4*>(STG + slot * STG_FLOATS) + lane;
               for (int it = 0; it < iters; it += 2) {
@@ -351,10 +354,12 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         mbar_wait(&halo_bar[i], (halo_par >> i) & 1);
         halo_par ^= 1u << i;
         const int nst = tile_streams(i), sg0 = i * spt;
-        if ((T & 3) == 0) {   // out_cache[b][c][off + j] = cat[c][T + j]   (mdtc.py:113); rows are 16-byte aligned
-          const int v4 = pad >> 2, n4 = nst * C * v4;
+        if (a.debug & 8) {
+        } else if ((T & 3) == 0) {   // out_cache[b][c][off + j] = cat[c][T + j]   (mdtc.py:113); rows are 16-byte aligned
+          // pad is a power of two here (tc_eligible): e -> (stream*64 + channel, float4 of the slice) by shifts
+          const int v4 = pad >> 2, n4 = nst * C * v4, sh = 31 - __clz(v4);
           for (int e = tid; e < n4; e += NCT) {
-            const int cs = e / v4, v = e - cs * v4, s = cs >> 6, c = cs & 63;
+            const int cs = e >> sh, v = e & (v4 - 1), s = cs >> 6, c = cs & 63;
             const float4 x4 = *reinterpret_cast<const float4*>(X + c * RPX + (sg0 + s) * Lw + PADR - pad + T + 4 * v);
             *reinterpret_cast<float4*>(a.out_cache + ((size_t)(b0 + sg0 + s) * C + c) * a.P + off + 4 * v) = x4;
           }
@@ -526,7 +531,10 @@ bool tc_eligible(const TcArgs& a, int padmax) {
   if (a.idim % 8 != 0 || a.idim > 128 || a.odim > 8 || a.ktaps > 5) return false;
   if (padmax > 32 || a.P % 4 != 0) return false;
   for (int b = 0; b < a.nblocks; ++b)
-    if ((a.dil[b] * (a.ktaps - 1)) % 4 != 0 || a.coff[b] % 4 != 0) return false;
+  {
+    const int pad = a.dil[b] * (a.ktaps - 1);
+    if (pad < 4 || (pad & (pad - 1)) != 0 || a.coff[b] % 4 != 0) return false;   // power-of-two slices, 16-byte aligned
+  }
   return true;
 }
 
