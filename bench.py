@@ -45,7 +45,11 @@ WORKLOADS = {
     "gru_b512_t1": ("gru", 512, 1, 80),
     "tcn_b1024_t40": ("tcn", 1024, 40, 80),
     "ds_tcn_b1024_t40": ("ds_tcn", 1024, 40, 80),
+    # BASELINE configs[4]: raw PCM -> posterior, 10 000 one-second clips over 8 GPUs = 1250 clips per GPU;
+    # T = 98 frames per clip (16000 samples), every clip starts a stream (no cache carried)
+    "pcm_e2e_1250x1s": ("mdtc", 1250, 98, 80),
 }
+PCM_SAMPLES = 16000
 NSETS = 4
 
 
@@ -214,8 +218,19 @@ def main():
     model = synth.randomize_(init_model(cfg), seed=777).eval().to(dev)
     gru = model_name == "gru"
     cshape = (2, B, 128) if gru else (B, model.hdim, model.backbone.padding)
-    feats = [synth.features(B, T, idim, seed=4321 + rank * 17 + s).to(dev) for s in range(NSETS)]
-    caches = [torch.zeros(cshape, device=dev) for _ in range(NSETS)]
+    pcm_mode = args.workload.startswith("pcm_")
+    if pcm_mode:
+        from wekws_b200 import Fbank
+        fb = Fbank(idim)
+        pcm = [synth.pcm_int16(B, PCM_SAMPLES, seed=1234 + rank * 17 + s).to(dev) for s in range(NSETS)]
+        feat_buf = torch.empty(B, T, idim, device=dev)
+        feats = [feat_buf] * NSETS
+        caches = [None] * NSETS
+        config["workload"] = (f"raw int16 PCM -> Fbank -> {model_name}: {B} one-second clips/GPU "
+                              f"({T} frames each), start of stream")
+    else:
+        feats = [synth.features(B, T, idim, seed=4321 + rank * 17 + s).to(dev) for s in range(NSETS)]
+        caches = [torch.zeros(cshape, device=dev) for _ in range(NSETS)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -226,7 +241,10 @@ def main():
     # ---------------- device-resident throughput (`value`) + per-launch durations (roofline) ----------
     def step(i):
         s = i % NSETS
-        _, caches[s] = model(feats[s], caches[s])
+        if pcm_mode:
+            model(fb(pcm[s], out=feat_buf))
+        else:
+            _, caches[s] = model(feats[s], caches[s])
 
     for i in range(args.warmup):
         step(i)
@@ -256,9 +274,9 @@ def main():
     fps = frames_total / (total_ms_max * 1e-3)
 
     # ---------------- end to end through the public API with host buffers (`e2e`) ----------------------
-    h_feats = [f.cpu().pin_memory() for f in feats]
+    h_feats = [(p if pcm_mode else f).cpu().pin_memory() for p, f in zip(pcm if pcm_mode else feats, feats)]
     h_out = [torch.empty(B, T, model.odim).pin_memory() for _ in range(2)]
-    d_in = [torch.empty_like(feats[0]) for _ in range(2)]
+    d_in = [torch.empty_like(pcm[0] if pcm_mode else feats[0]) for _ in range(2)]
     copy_stream, main_stream = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
@@ -279,7 +297,10 @@ def main():
                     d_in[nb].copy_(h_feats[(i + 1) % NSETS], non_blocking=True)
                     in_ready[nb].record(copy_stream)
             main_stream.wait_event(in_ready[b])
-            y, caches[s] = model(d_in[b], caches[s])
+            if pcm_mode:
+                y, _ = model(fb(d_in[b], out=feat_buf))
+            else:
+                y, caches[s] = model(d_in[b], caches[s])
             in_free[b].record(main_stream)
             h_out[b].copy_(y, non_blocking=True)
         main_stream.synchronize()
@@ -325,7 +346,11 @@ def main():
 
     peak, peak_src = measured_peaks()
     bpf = algorithmic_bytes_per_frame(model_name, T, idim, model.odim)
+    if pcm_mode:   # PCM in + posteriors out + the new cache written once (no cache read at start of stream)
+        bpf = PCM_SAMPLES * 2.0 / T + model.odim * 4 + (64 * 244 * 4) / T
     launch_ms = statistics.mean(per_launch_ms)
+    srt = sorted(per_launch_ms)
+    p99_ms = srt[min(len(srt) - 1, int(0.99 * len(srt)))]
     achieved = bpf * B * T / (launch_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "dominant_kernel.json")
@@ -342,17 +367,18 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "frames_per_sec": fps,
-        "p50_step_latency_ms": statistics.median(per_launch_ms),
+        "p50_step_latency_ms": statistics.median(per_launch_ms), "p99_step_latency_ms": p99_ms,
         "p50_chunk_latency_ms_1stream": lat,
         "clocks": clocks,
         "e2e": {"value": e2e_fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "frames_per_sec": e2e_fps,
-                "h2d_bytes_per_step": B * T * idim * 4, "d2h_bytes_per_step": B * T * model.odim * 4,
+                "h2d_bytes_per_step": (B * PCM_SAMPLES * 2) if pcm_mode else (B * T * idim * 4),
+                "d2h_bytes_per_step": B * T * model.odim * 4,
                 "ms_per_step": float(t.item()) / e2e_steps,
                 "api": "wekws_b200.KWSModel.forward(feats, cache); pinned host feats in, posteriors out, "
                        "H2D double-buffered on a copy stream"},
         "gpu_launches": launches,
         "tensor_cores": bool(model.uses_tensor_cores(T)),
-        "roofline": {"kernel": ("mdtc_tc_kernel" if model.uses_tensor_cores(T) else "conv_backbone_kernel") if not gru else "gru_kernel", "bound": "hbm",
+        "roofline": {"kernel": ("fbank_kernel + " if pcm_mode else "") + (("mdtc_tc_kernel" if model.uses_tensor_cores(T) else "conv_backbone_kernel") if not gru else "gru_kernel"), "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src + ", burst", "traffic": traffic,
                      "algorithmic_bytes_per_frame": bpf, "launch_ms": launch_ms,

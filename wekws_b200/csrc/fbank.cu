@@ -11,7 +11,7 @@
 // even/odd packed frame, done as a radix-8 / radix-8 / radix-4 Stockham autosort with the
 // first radix-8 entirely in registers (lane p holds z[p + 32 r]) and two exchanges through
 // bank-conflict-free padded per-warp shared buffers; lane-constant twiddles live in
-// registers.  A CTA (8 warps) stages the 1520 samples its 8 consecutive frames need once
+// registers.  A CTA (8 warps) stages the 5360 samples its 32 consecutive frames need once
 // (coalesced), so each PCM byte is read from HBM ~1.05x and each output byte written once.
 #include <math.h>
 #include <vector>
@@ -22,10 +22,12 @@ namespace wekws {
 
 namespace {
 
-constexpr int FB_WARPS = 8;                 // frames per CTA work item
+constexpr int FB_WARPS = 8;                 // warps per CTA
+constexpr int FB_FPW = 4;                   // frames per warp per work item
+constexpr int FB_FRAMES = FB_WARPS * FB_FPW; // frames per CTA work item (one staging load)
 constexpr int FB_NT = FB_WARPS * 32;
 constexpr int WIN = 400, SHIFT = 160, NFFT = 512, NBIN = 256;
-constexpr int STAGE = (FB_WARPS - 1) * SHIFT + WIN;   // 1520 samples
+constexpr int STAGE = (FB_FRAMES - 1) * SHIFT + WIN;  // 5360 samples
 constexpr int A_SZ = 264, B_SZ = 280;       // padded exchange buffers (floats)
 constexpr int MAX_MEL = 128;
 
@@ -82,12 +84,13 @@ __device__ __forceinline__ void dft8(float (&r)[8], float (&i)[8]) {
 
 template <typename PCM>
 __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
-  __shared__ float s_stage[STAGE];
-  __shared__ float s_bufA[FB_WARPS][2][A_SZ];
-  __shared__ float s_bufB[FB_WARPS][2][B_SZ];
-  __shared__ float2 s_tw512[NBIN];
-  __shared__ float2 s_win[WIN / 2];
-  __shared__ float s_mw[2 * NBIN + 64];
+  extern __shared__ __align__(16) float fb_smem[];
+  float* s_stage = fb_smem;                                              // [STAGE]
+  float (*s_bufA)[2][A_SZ] = reinterpret_cast<float (*)[2][A_SZ]>(s_stage + STAGE);
+  float (*s_bufB)[2][B_SZ] = reinterpret_cast<float (*)[2][B_SZ]>(s_stage + STAGE + FB_WARPS * 2 * A_SZ);
+  float2* s_tw512 = reinterpret_cast<float2*>(s_stage + STAGE + FB_WARPS * 2 * (A_SZ + B_SZ));
+  float2* s_win = s_tw512 + NBIN;
+  float* s_mw = reinterpret_cast<float*>(s_win + WIN / 2);               // [2 * NBIN + 64]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < NBIN; i += FB_NT) s_tw512[i] = a.tw512[i];
@@ -106,11 +109,11 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
   float* Ar = s_bufA[warp][0]; float* Ai = s_bufA[warp][1];
   float* Br = s_bufB[warp][0]; float* Bi = s_bufB[warp][1];
 
-  const long long nfb = (a.max_frames + FB_WARPS - 1) / FB_WARPS;
+  const long long nfb = (a.max_frames + FB_FRAMES - 1) / FB_FRAMES;
   const long long items = a.B * nfb;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const long long b = item / nfb;
-    const long long f0 = (item - b * nfb) * FB_WARPS;
+    const long long f0 = (item - b * nfb) * FB_FRAMES;
     long long len = a.lens ? (long long)a.lens[b] : a.num_samples;
     if (len > a.num_samples) len = a.num_samples;
     long long mb = len < WIN ? 0 : 1 + (len - WIN) / SHIFT;
@@ -127,8 +130,10 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
     }
     __syncthreads();
 
-    const long long f = f0 + warp;
-    if (f >= a.max_frames) continue;          // warp-uniform; no block barrier below in this iteration
+    for (int fi = 0; fi < FB_FPW; ++fi) {
+    const int fl = warp + FB_WARPS * fi;          // frame of this warp within the item
+    const long long f = f0 + fl;
+    if (f >= a.max_frames) continue;          // warp-uniform; no block barrier inside this loop
     float* outp = a.out + (b * a.max_frames + f) * a.nmel;
     if (f >= mb) {
       for (int m = lane; m < a.nmel; m += 32) outp[m] = 0.f;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
     }
 
     // ---- window: lane owns packed points m = lane + 32 i (even/odd sample pair 2m, 2m+1) ----
-    const float* s = s_stage + warp * SHIFT;
+    const float* s = s_stage + fl * SHIFT;
     float xa[7], xb[7], xc[7];
     float sum = 0.f;
 #pragma unroll
@@ -237,6 +242,7 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
       outp[m] = v;
     }
     __syncwarp();
+    }   // frames of this warp
   }
 }
 
@@ -340,13 +346,26 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.tw256 = fb->d_tw256; a.tw512 = fb->d_tw512; a.window = fb->d_window;
   a.mstart = fb->d_mstart; a.mcnt = fb->d_mcnt; a.moff = fb->d_moff; a.mw = fb->d_mw;
   a.mw_total = fb->mw_total;
-  const long long items = B * ((max_frames + FB_WARPS - 1) / FB_WARPS);
-  const long long cap = (long long)device_sm_count() * 4;
+  const long long items = B * ((max_frames + FB_FRAMES - 1) / FB_FRAMES);
+  const size_t smem = (size_t)(STAGE + FB_WARPS * 2 * (A_SZ + B_SZ) + 2 * NBIN + WIN + 2 * NBIN + 64) * sizeof(float);
+  static int occ[2] = {0, 0};
+  const int ti = pcm_dtype == WEKWS_PCM_S16 ? 0 : 1;
+  if (occ[ti] == 0) {
+    if (ti == 0) {
+      WEKWS_CUDA_OK(cudaFuncSetAttribute(fbank_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      WEKWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[ti], fbank_kernel<int16_t>, FB_NT, smem));
+    } else {
+      WEKWS_CUDA_OK(cudaFuncSetAttribute(fbank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      WEKWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[ti], fbank_kernel<float>, FB_NT, smem));
+    }
+    if (occ[ti] < 1) occ[ti] = 1;
+  }
+  const long long cap = (long long)device_sm_count() * occ[ti];
   const int grid = (int)(items < cap ? items : cap);
   cudaStream_t st = (cudaStream_t)stream;
   if (pcm_dtype == WEKWS_PCM_S16)
-    fbank_kernel<int16_t><<<grid, FB_NT, 0, st>>>(a);
+    fbank_kernel<int16_t><<<grid, FB_NT, smem, st>>>(a);
   else
-    fbank_kernel<float><<<grid, FB_NT, 0, st>>>(a);
+    fbank_kernel<float><<<grid, FB_NT, smem, st>>>(a);
   return check_launch("fbank_kernel");
 }
