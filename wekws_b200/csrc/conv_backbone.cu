@@ -94,41 +94,60 @@ struct TileMap {
   ACC[14] = fmaf(W4.w, A4.z, ACC[14]); ACC[15] = fmaf(W4.w, A4.w, ACC[15]);
 
 // acc[t][i*4+j] += sum_k W[k][o0+i] * A[k][r0[t]+j]     (A channel-major: [K][RP])
-template <int C>
-__device__ __forceinline__ void gemm_cm(float (&acc)[TPT][16], const float* __restrict__ A, int RP,
-                                        const float* __restrict__ W, int K, const TileMap<C>& tm) {
+// RP is a multiple of 16, so a warp's four row groups are valid or padding together (no divergence).
+template <int C, bool TWO>
+__device__ __forceinline__ void gemm_cm_impl(float (&acc)[TPT][16], const float* __restrict__ A, int RP,
+                                             const float* __restrict__ W, int K, const TileMap<C>& tm) {
   const float* wp = W + tm.o0;
-#pragma unroll 4
+  const float* a0 = A + tm.r0[0];
+  const float* a1 = A + tm.r0[1];
+#pragma unroll 8
   for (int k = 0; k < K; ++k) {
-    const float4 w4 = *reinterpret_cast<const float4*>(wp + k * C);
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-      if (tm.valid[t]) {
-        const float4 a4 = *reinterpret_cast<const float4*>(A + k * RP + tm.r0[t]);
-        FMA16(acc[t], w4, a4)
-      }
+    const float4 w4 = *reinterpret_cast<const float4*>(wp);
+    wp += C;
+    const float4 x0 = *reinterpret_cast<const float4*>(a0);
+    a0 += RP;
+    FMA16(acc[0], w4, x0)
+    if (TWO) {
+      const float4 x1 = *reinterpret_cast<const float4*>(a1);
+      a1 += RP;
+      FMA16(acc[1], w4, x1)
     }
   }
 }
+template <int C>
+__device__ __forceinline__ void gemm_cm(float (&acc)[TPT][16], const float* __restrict__ A, int RP,
+                                        const float* __restrict__ W, int K, const TileMap<C>& tm) {
+  if (tm.valid[1]) gemm_cm_impl<C, true>(acc, A, RP, W, K, tm);
+  else if (tm.valid[0]) gemm_cm_impl<C, false>(acc, A, RP, W, K, tm);
+}
 
 // Same with A row-major: A[r][KP] (first Linear: frames x idim), column offset k0.
+template <int C, bool TWO>
+__device__ __forceinline__ void gemm_rm_impl(float (&acc)[TPT][16], const float* __restrict__ A, int KP,
+                                             const float* __restrict__ W, int K, const TileMap<C>& tm) {
+  const float* wp = W + tm.o0;
+  const float* a0 = A + tm.r0[0] * KP;
+  const float* a1 = A + tm.r0[1] * KP;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wp);
+    wp += C;
+    float4 x0;
+    x0.x = a0[k]; x0.y = a0[KP + k]; x0.z = a0[2 * KP + k]; x0.w = a0[3 * KP + k];
+    FMA16(acc[0], w4, x0)
+    if (TWO) {
+      float4 x1;
+      x1.x = a1[k]; x1.y = a1[KP + k]; x1.z = a1[2 * KP + k]; x1.w = a1[3 * KP + k];
+      FMA16(acc[1], w4, x1)
+    }
+  }
+}
 template <int C>
 __device__ __forceinline__ void gemm_rm(float (&acc)[TPT][16], const float* __restrict__ A, int KP,
                                         const float* __restrict__ W, int K, const TileMap<C>& tm) {
-  const float* wp = W + tm.o0;
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 w4 = *reinterpret_cast<const float4*>(wp + k * C);
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-      if (tm.valid[t]) {
-        const float* ap = A + tm.r0[t] * KP + k;
-        float4 a4;
-        a4.x = ap[0]; a4.y = ap[KP]; a4.z = ap[2 * KP]; a4.w = ap[3 * KP];
-        FMA16(acc[t], w4, a4)
-      }
-    }
-  }
+  if (tm.valid[1]) gemm_rm_impl<C, true>(acc, A, KP, W, K, tm);
+  else if (tm.valid[0]) gemm_rm_impl<C, false>(acc, A, KP, W, K, tm);
 }
 
 __device__ __forceinline__ void zero_acc(float (&acc)[TPT][16]) {
@@ -211,6 +230,15 @@ __global__ void __launch_bounds__(NT, 1) conv_backbone_kernel(const ConvArgs a) 
     const int b0 = tile * S;
     const int Sv = min(S, a.B - b0);           // valid streams in this tile
     const int ROWS = Sv * T;
+    // rows owned by this lane in the time-parallel loops: r = lane + 32*qi  ->  (stream, frame); -1 = padding row
+    int row_s[8], row_t[8];
+#pragma unroll
+    for (int qi = 0; qi < 8; ++qi) {
+      const int r = lane + 32 * qi;
+      const int sidx = r / T;
+      row_s[qi] = r < ROWS ? sidx : -1;
+      row_t[qi] = r - sidx * T;
+    }
 
     // issue the cache slice of block `blk` into halo (zero when no cache / invalid stream)
     auto issue_halo = [&](int blk) -> int {
@@ -278,13 +306,15 @@ __global__ void __launch_bounds__(NT, 1) conv_backbone_kernel(const ConvArgs a) 
           float* buf = (j & 1) ? hbuf : abuf;
           for (int c = warp; c < C; c += NT / 32) {
             const float* xrow = xbuf + c * RP;
-            for (int r = lane; r < RP; r += 32) {
-              float v = 0.f;
-              if (r < ROWS) {
-                const int s = r / T, t = r - s * T;
-                v = cat_at(xrow, halo + (c * S + s) * PADMAX, s, T, pad, t + j * d);
+#pragma unroll
+            for (int qi = 0; qi < 8; ++qi) {
+              const int r = lane + 32 * qi;
+              if (r < RP) {
+                float v = 0.f;
+                if (row_s[qi] >= 0)
+                  v = cat_at(xrow, halo + (c * S + row_s[qi]) * PADMAX, row_s[qi], T, pad, row_t[qi] + j * d);
+                buf[c * RP + r] = v;
               }
-              buf[c * RP + r] = v;
             }
           }
           for (int k0 = 0; k0 < C; k0 += WPipe<C>::KC) {
@@ -304,18 +334,22 @@ __global__ void __launch_bounds__(NT, 1) conv_backbone_kernel(const ConvArgs a) 
           for (int j = 0; j < 8; ++j) wt[j] = j < K ? __ldg(vb + j * C + c) : 0.f;
           const float bias = __ldg(vb + K * C + c);
           const float* xrow = xbuf + c * RP;
-          for (int r = lane; r < RP; r += 32) {
-            float v = 0.f;
-            if (r < ROWS) {
-              const int s = r / T, t = r - s * T;
-              const float* hrow = halo + (c * S + s) * PADMAX;
-              v = bias;
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (j < K) v = fmaf(wt[j], cat_at(xrow, hrow, s, T, pad, t + j * d), v);
-              if (dw_relu) v = fmaxf(v, 0.f);
+          for (int qi = 0; qi < 8; ++qi) {
+            const int r = lane + 32 * qi;
+            if (r < RP) {
+              float v = 0.f;
+              if (row_s[qi] >= 0) {
+                const int sidx = row_s[qi], t = row_t[qi];
+                const float* hrow = halo + (c * S + sidx) * PADMAX;
+                v = bias;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j < K) v = fmaf(wt[j], cat_at(xrow, hrow, sidx, T, pad, t + j * d), v);
+                if (dw_relu) v = fmaxf(v, 0.f);
+              }
+              abuf[c * RP + r] = v;
             }
-            abuf[c * RP + r] = v;
           }
         }
         const float* vb1 = vb + (K + 1) * C;
@@ -409,7 +443,7 @@ int conv_backbone_max_T(const ConvArgs& a, int padmax_raw) {
   int best = 0;
   for (int T = 1; T <= max_rows_map(a.C); ++T) {
     size_t ah;
-    const int RP = (T + 3) & ~3;
+    const int RP = (T + 15) & ~15;
     if (RP > max_rows_map(a.C) || tile_smem(a, 1, RP, padmax_raw, KP, &ah) > kSmemCap) break;
     best = T;
   }
@@ -426,7 +460,7 @@ int conv_backbone_launch(ConvArgs a, int padmax_raw, cudaStream_t st) {
   // largest S that fits the tile map and shared memory
   int smax = 0;
   for (int S = 1; S <= a.B; ++S) {
-    const int RP = (S * a.T + 3) & ~3;
+    const int RP = (S * a.T + 15) & ~15;
     size_t ah;
     if (RP > max_rows_map(C) || tile_smem(a, S, RP, a.PADMAX, a.KP, &ah) > kSmemCap) break;
     smax = S;
@@ -439,11 +473,11 @@ int conv_backbone_launch(ConvArgs a, int padmax_raw, cudaStream_t st) {
   for (int S = 1; S <= smax; ++S) {
     const long tiles = (a.B + S - 1) / S;
     const long waves = (tiles + sms - 1) / sms;
-    const long cost = waves * ((((long)S * a.T + 3) & ~3L) + 24);   // +24: fixed per-tile overhead in row units
+    const long cost = waves * ((((long)S * a.T + 15) & ~15L) + 24);   // +24: fixed per-tile overhead in row units
     if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = S; }
   }
   a.S = best;
-  a.RP = (a.S * a.T + 3) & ~3;
+  a.RP = (a.S * a.T + 15) & ~15;
   size_t ah;
   const size_t smem = tile_smem(a, a.S, a.RP, a.PADMAX, a.KP, &ah);
   a.ah_floats = (int)ah;
