@@ -92,8 +92,8 @@ def eval_gru(vec, H, L, idim, odim, act_sigmoid, has_cmvn, x, h0):
         inp = xin[:, t]
         for l in range(L):
             base = v_layers + l * stride
-            wih = vec[base:base + H * G].reshape(H, G)
-            whh = vec[base + H * G:base + 2 * H * G].reshape(H, G)
+            w2 = vec[base:base + 2 * H * G].reshape(H, 2 * G)       # row k: [W_ih[:, k] | W_hh[:, k]]
+            wih, whh = w2[:, :G], w2[:, G:]
             gi = inp @ wih + vec[base + 2 * H * G: base + 2 * H * G + G]
             gh = h[l] @ whh + vec[base + 2 * H * G + G: base + 2 * H * G + 2 * G]
             r = torch.sigmoid(gi[:, :H] + gh[:, :H])

@@ -362,10 +362,10 @@ int pack_gru(wekws_model* m) {
     GET(whh, "backbone.weight_hh" + sfx, (size_t)G * H);
     GET(bih, "backbone.bias_ih" + sfx, (size_t)G);
     GET(bhh, "backbone.bias_hh" + sfx, (size_t)G);
-    for (int k = 0; k < H; ++k)
+    for (int k = 0; k < H; ++k) {            // row k: [W_ih[:, k] | W_hh[:, k]]  (768 floats, streamed by TMA)
       for (int g = 0; g < G; ++g) m->h_vec.push_back(wih[g * H + k]);
-    for (int k = 0; k < H; ++k)
       for (int g = 0; g < G; ++g) m->h_vec.push_back(whh[g * H + k]);
+    }
     m->h_vec.insert(m->h_vec.end(), bih, bih + G);
     m->h_vec.insert(m->h_vec.end(), bhh, bhh + G);
   }

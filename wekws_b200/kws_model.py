@@ -236,15 +236,17 @@ class KWSModel(nn.Module):
             raise ValueError(f"features must be (B, T, {self.idim}), got {tuple(x.shape)}")
         dev = x.device
         B, T = x.size(0), x.size(1)
-        x = x.contiguous()
+        if not x.is_contiguous():
+            x = x.contiguous()
         gru = isinstance(self.backbone, nn.GRU)
         cache_shape = (self.backbone.num_layers, B, self.hdim) if gru else (B, self.hdim, self.backbone.padding)
         cache_ptr = None
         if in_cache is not None and in_cache.numel() > 0:
             if tuple(in_cache.shape) != cache_shape:
                 raise ValueError(f"in_cache must be {cache_shape}, got {tuple(in_cache.shape)}")
-            in_cache = in_cache.to(device=dev, dtype=torch.float32).contiguous()
-            cache_ptr = C.c_void_p(in_cache.data_ptr())
+            if in_cache.device != dev or in_cache.dtype != torch.float32 or not in_cache.is_contiguous():
+                in_cache = in_cache.to(device=dev, dtype=torch.float32).contiguous()
+            cache_ptr = in_cache.data_ptr()
         h = self._ensure(dev)
         if self._precision_applied != self.precision:
             if self.precision not in ("auto", "fp32"):
@@ -252,7 +254,7 @@ class KWSModel(nn.Module):
             _native.check(_native.lib().wekws_model_set_precision(h, 0 if self.precision == "auto" else 1),
                           "wekws_model_set_precision")
             self._precision_applied = self.precision
-        out = torch.empty(B, T, self.odim, device=dev, dtype=torch.float32)
+        out = torch.empty((B, T, self.odim), device=dev, dtype=torch.float32)
         if T == 0 and cache_ptr is not None:
             out_cache = in_cache.clone()
         elif T == 0:
@@ -260,12 +262,16 @@ class KWSModel(nn.Module):
         else:
             out_cache = torch.empty(cache_shape, device=dev, dtype=torch.float32)
         if B > 0 and T > 0:
-            with torch.cuda.device(dev):
-                stream = torch.cuda.current_stream(dev).cuda_stream
-                rc = _native.lib().wekws_model_forward(
-                    h, C.c_void_p(x.data_ptr()), cache_ptr, C.c_void_p(out.data_ptr()),
-                    C.c_void_p(out_cache.data_ptr()), B, T, flags, C.c_void_p(stream))
-            _native.check(rc, "wekws_model_forward")
+            fwd = _native.lib().wekws_model_forward
+            if torch.cuda.current_device() == dev.index:          # common case: no device switch needed
+                rc = fwd(h, x.data_ptr(), cache_ptr, out.data_ptr(), out_cache.data_ptr(), B, T, flags,
+                         torch.cuda.current_stream(dev).cuda_stream)
+            else:
+                with torch.cuda.device(dev):
+                    rc = fwd(h, x.data_ptr(), cache_ptr, out.data_ptr(), out_cache.data_ptr(), B, T, flags,
+                             torch.cuda.current_stream(dev).cuda_stream)
+            if rc != 0:
+                _native.check(rc, "wekws_model_forward")
         return out, out_cache
 
     def forward(self, x: torch.Tensor, in_cache: torch.Tensor = _EMPTY) -> Tuple[torch.Tensor, torch.Tensor]:
