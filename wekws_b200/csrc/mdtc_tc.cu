@@ -278,6 +278,23 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       const bool q_live[NTILE] = {32 * q < rows_i[0], 32 * q < rows_i[1], 32 * q < rows_i[2]};
       const uint32_t tm_row = tmem + ((uint32_t)(32 * q) << 16);
       const uint32_t xs = sbase + OFF_X;
+      // Cache stores go to the warps with the least depthwise work: lane quarters that are padding in some tile
+      // (e.g. tiles of 120/120/40 rows: quarters 2,3 skip tile 2).  If every quarter is equally busy, all store.
+      int nlive[4], maxlive = 0, minlive = NTILE;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        nlive[qq] = (32 * qq < rows_i[0]) + (32 * qq < rows_i[1]) + (32 * qq < rows_i[2]);
+        maxlive = max(maxlive, nlive[qq]);
+        minlive = min(minlive, nlive[qq]);
+      }
+      int nhq = 0, myrank = -1;                        // helper quarters and this warp's rank among them
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const bool helper = (maxlive == minlive) || (nlive[qq] == minlive);
+        if (helper) { if (qq == q) myrank = nhq; ++nhq; }
+      }
+      const int n_store_thr = nhq * 4 * 32;            // 4 warps (g = 0..3) per quarter
+      const int store_idx = myrank < 0 ? -1 : (g * nhq + myrank) * 32 + lane;
       float part[NTILE][8];                          // classifier partial sums over this thread's 16 channels
 #pragma unroll
       for (int i = 0; i < NTILE; ++i)
@@ -353,27 +370,6 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         }
         mbar_wait(&halo_bar[i], (halo_par >> i) & 1);
         halo_par ^= 1u << i;
-        const int nst = tile_streams(i), sg0 = i * spt;
-        if (a.debug & 8) {
-        } else if ((T & 3) == 0) {   // out_cache[b][c][off + j] = cat[c][T + j]   (mdtc.py:113); rows are 16-byte aligned
-          // pad is a power of two here (tc_eligible): e -> (stream*64 + channel, float4 of the slice) by shifts
-          const int v4 = pad >> 2, n4 = nst * C * v4, sh = 31 - __clz(v4);
-          for (int e = tid; e < n4; e += NCT) {
-            const int cs = e >> sh, v = e & (v4 - 1), s = cs >> 6, c = cs & 63;
-            const float4 x4 = *reinterpret_cast<const float4*>(X + c * RPX + (sg0 + s) * Lw + PADR - pad + T + 4 * v);
-            *reinterpret_cast<float4*>(a.out_cache + ((size_t)(b0 + sg0 + s) * C + c) * a.P + off + 4 * v) = x4;
-          }
-        } else {
-          int npw = 4;
-          while (npw < pad) npw <<= 1;
-          const int j = tid & (npw - 1), step = NCT / npw, nrow = nst * C;
-          if (j < pad) {
-            for (int cs = tid / npw; cs < nrow; cs += step) {
-              const int s = cs >> 6, c = cs & 63;
-              a.out_cache[((size_t)(b0 + sg0 + s) * C + c) * a.P + off + j] = X[c * RPX + (sg0 + s) * Lw + PADR - pad + T + j];
-            }
-          }
-        }
         if (q_live[i] && !(a.debug & 2)) {
           // this warp: rows 32q.., channel groups g and g + 4; tap j of channel c reads X[c][col - pad + j*d]
 #pragma unroll
@@ -405,7 +401,34 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           }
         }
         hand_over(tc);
-        if (lane == 0) mbar_arrive(&h_free[i]);      // (after the __syncwarp in hand_over) cache columns consumed
+      };
+      // new cache slices of every tile: out_cache[b][c][off + j] = cat[c][T + j]   (mdtc.py:113), by the helper warps;
+      // then every warp releases the tiles' cache columns to the loaders.  All of this precedes the warp's EPI1
+      // hand-overs, hence the conv2 GEMMs and EPI2 (which overwrites x) cannot start before the stores are done.
+      auto store_cache = [&](int blk) {
+        const int d = a.dil[blk], pad = d * (K - 1), off = a.coff[blk];
+        if (store_idx >= 0 && !(a.debug & 8)) {
+          for (int i = 0; i < ntile; ++i) {
+            const int nst = tile_streams(i), sg0 = i * spt;
+            if ((T & 3) == 0) {      // rows are 16-byte aligned; pad is a power of two (tc_eligible)
+              const int v4 = pad >> 2, n4 = nst * C * v4, sh = 31 - __clz(v4);
+              for (int e = store_idx; e < n4; e += n_store_thr) {
+                const int cs = e >> sh, v = e & (v4 - 1), s = cs >> 6, c = cs & 63;
+                const float4 x4 = *reinterpret_cast<const float4*>(X + c * RPX + (sg0 + s) * Lw + PADR - pad + T + 4 * v);
+                *reinterpret_cast<float4*>(a.out_cache + ((size_t)(b0 + sg0 + s) * C + c) * a.P + off + 4 * v) = x4;
+              }
+            } else {
+              const int n = nst * C * pad, sh = 31 - __clz(pad);
+              for (int e = store_idx; e < n; e += n_store_thr) {
+                const int cs = e >> sh, j = e & (pad - 1), s = cs >> 6, c = cs & 63;
+                a.out_cache[((size_t)(b0 + sg0 + s) * C + c) * a.P + off + j] = X[c * RPX + (sg0 + s) * Lw + PADR - pad + T + j];
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (int i = 0; i < ntile; ++i) mbar_arrive(&h_free[i]);
       };
       // h = relu(D + b1) -> operand rows of tile i in TMEM                  (mdtc.py:115)
       auto epi1 = [&](auto tc, int blk) {
@@ -483,6 +506,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         dw(T0, blk);
         if (ntile > 1) dw(T1, blk);
         if (ntile > 2) dw(T2, blk);
+        store_cache(blk);
         epi1(T0, blk);
         if (ntile > 1) epi1(T1, blk);
         if (ntile > 2) epi1(T2, blk);
