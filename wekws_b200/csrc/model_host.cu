@@ -18,6 +18,7 @@
 #include "conv_backbone.h"
 #include "gru.h"
 #include "mdtc_tc.h"
+#include "tcn_tc.h"
 
 namespace wekws {
 
@@ -93,6 +94,8 @@ struct wekws_model {
   bool tc_ok = false;
   int precision = 0;                        // 0 auto (tensor cores where eligible), 1 fp32 FFMA only
   TcArgs tcargs{};
+  bool tcn_ok = false;                      // tensor-core path for the dense TCN (hidden 64)
+  TcnTcArgs tcnargs{};
 };
 
 namespace {
@@ -212,8 +215,28 @@ void write_w_image(uint8_t* dst, const std::vector<float>& wt /*[K][64]*/, int K
 // Tensor-core eligibility + pre-swizzled bf16x3 weight images (mdtc_tc.cu)
 void pack_tc(wekws_model* m) {
   m->tc_ok = false;
+  m->tcn_ok = false;
   m->h_wimg.clear();
   const wekws_model_config& c = m->cfg;
+  if (c.backbone == WEKWS_BACKBONE_TCN && c.hdim == 64) {
+    TcnTcArgs& t = m->tcnargs;
+    memset(&t, 0, sizeof(t));
+    const ConvArgs& a = m->conv;
+    t.idim = a.idim; t.odim = a.odim; t.nblocks = a.nblocks; t.ktaps = a.ktaps; t.P = a.P;
+    t.act = a.act; t.has_cmvn = a.has_cmvn;
+    t.v_mean = a.v_mean; t.v_istd = a.v_istd; t.v_bp = a.v_bp; t.v_blocks = a.v_blocks;
+    t.v_blk_stride = a.v_blk_stride; t.v_wc = a.v_wc; t.v_bc = a.v_bc;
+    for (int b = 0; b < a.nblocks; ++b) { t.dil[b] = a.dil[b]; t.coff[b] = a.coff[b]; }
+    if (!tcn_tc_eligible(t, m->padmax)) return;
+    if (m->folded.size() != (size_t)(1 + a.ktaps * a.nblocks)) return;
+    m->h_wimg.assign((size_t)(2 + a.ktaps * a.nblocks) * 16384, 0);
+    write_w_image(m->h_wimg.data(), m->folded[0], a.idim, 0);
+    if (a.idim > 64) write_w_image(m->h_wimg.data() + 16384, m->folded[0], a.idim, 64);
+    for (int g = 0; g < a.ktaps * a.nblocks; ++g)
+      write_w_image(m->h_wimg.data() + (size_t)(2 + g) * 16384, m->folded[1 + g], 64, 0);
+    m->tcn_ok = true;
+    return;
+  }
   if (c.backbone != WEKWS_BACKBONE_MDTC || c.hdim != 64) return;
   TcArgs& t = m->tcargs;
   memset(&t, 0, sizeof(t));
@@ -447,10 +470,11 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
     WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_chunk_off, m->h_chunk_off.size() * sizeof(int)));
     WEKWS_CUDA_OK(cudaMemcpy(m->d_chunk_off, m->h_chunk_off.data(), m->h_chunk_off.size() * sizeof(int), cudaMemcpyHostToDevice));
     m->conv.wstream = m->d_stream; m->conv.chunk_off = m->d_chunk_off; m->conv.vec = m->d_vec;
-    if (m->tc_ok) {
+    if (m->tc_ok || m->tcn_ok) {
       WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_wimg, m->h_wimg.size()));
       WEKWS_CUDA_OK(cudaMemcpy(m->d_wimg, m->h_wimg.data(), m->h_wimg.size(), cudaMemcpyHostToDevice));
       m->tcargs.wimg = m->d_wimg; m->tcargs.vec = m->d_vec;
+      m->tcnargs.wimg = m->d_wimg; m->tcnargs.vec = m->d_vec;
     }
     m->conv_max_T = conv_backbone_max_T(m->conv, m->padmax);
     WEKWS_REQUIRE(m->conv_max_T >= 1, "model does not fit the fused kernel's shared memory");
@@ -468,7 +492,7 @@ extern "C" int wekws_model_set_precision(wekws_model* m, int mode) {
 }
 
 extern "C" int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T) {
-  return (m && m->finalized && m->tc_ok && m->precision == 0 && T >= 8) ? 1 : 0;
+  return (m && m->finalized && (m->tc_ok || m->tcn_ok) && m->precision == 0 && T >= 8) ? 1 : 0;
 }
 
 extern "C" int64_t wekws_model_packed_floats(const wekws_model* m, int which) {
@@ -509,7 +533,8 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
     const bool use_tc = m->tc_ok && m->precision == 0 && T >= 8 &&
                         (d_in_cache == nullptr || ((uintptr_t)d_in_cache & 15) == 0) &&
                         ((uintptr_t)d_feats & 15) == 0 && ((uintptr_t)d_out_cache & 15) == 0;
-    const int maxT = use_tc ? tc_max_T() : m->conv_max_T;
+    const bool use_tcn = m->tcn_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
+    const int maxT = use_tc ? tc_max_T() : use_tcn ? tcn_tc_max_T() : m->conv_max_T;
     const int nchunk = (int)((T + maxT - 1) / maxT);
     const int Tc = (int)((T + nchunk - 1) / nchunk);
     for (int64_t t0 = 0; t0 < T; t0 += Tc) {
@@ -524,6 +549,20 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
         a.feat_bstride = T * m->cfg.idim;
         a.out_bstride = T * m->cfg.odim;
         int rc = mdtc_tc_launch(a, m->padmax, st);
+        if (rc) return rc;
+        continue;
+      }
+      if (use_tcn) {
+        TcnTcArgs a = m->tcnargs;
+        a.feats = d_feats + t0 * m->cfg.idim;
+        a.out = d_out + t0 * m->cfg.odim;
+        a.in_cache = t0 == 0 ? d_in_cache : d_out_cache;
+        a.out_cache = d_out_cache;
+        a.B = (int)B;
+        a.T = (int)(T - t0 < Tc ? T - t0 : Tc);
+        a.feat_bstride = T * m->cfg.idim;
+        a.out_bstride = T * m->cfg.odim;
+        int rc = tcn_tc_launch(a, m->padmax, st);
         if (rc) return rc;
         continue;
       }

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace wekws {
 namespace tc {
@@ -33,6 +34,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef WEKWS_MBAR_WATCHDOG
+// debug build: a wait that never completes reports which barrier it was (plus every warp's last progress mark)
+// and traps instead of hanging the GPU
+static __device__ int wd_marks[256][20];
+__device__ __forceinline__ void wd_mark(int v) {
+  if ((threadIdx.x & 31) == 0) *(volatile int*)&wd_marks[blockIdx.x & 255][(threadIdx.x >> 5) % 20] = v;
+}
+static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (long long spin = 0; spin < (1ll << 22); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) {
+    volatile int* m = wd_marks[0];
+    printf("mbar_wait timeout: thread %d barrier@smem 0x%x parity %u marks c0 %d c1 %d c2 %d c3 %d c4 %d c8 %d c12 %d c15 %d iss %d ld0 %d ld1 %d\n",
+           (int)threadIdx.x, smem_u32(bar), parity, m[0], m[1], m[2], m[3], m[4], m[8], m[12], m[15], m[16], m[17], m[18]);
+  }
+  for (int i = 0; i < 2000; ++i) __nanosleep(100000);       // let the other waiters report too
+  __trap();
+}
+#else
+__device__ __forceinline__ void wd_mark(int) {}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -45,9 +77,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+#endif
 
 // same, for single-lane service warps: back off between polls so the spin does not eat issue slots
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+#ifdef WEKWS_MBAR_WATCHDOG
+  mbar_wait(bar, parity);
+  return;
+#endif
   uint32_t done = 0;
   while (true) {
     asm volatile(
