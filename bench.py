@@ -384,7 +384,7 @@ def main():
                        "H2D double-buffered on a copy stream"},
         "gpu_launches": launches,
         "tensor_cores": bool(model.uses_tensor_cores(T)),
-        "roofline": {"kernel": ("fbank_kernel + " if pcm_mode else "") + ((("tcn_tc_kernel" if model_name == "tcn" else "mdtc_tc_kernel") if model.uses_tensor_cores(T) else "conv_backbone_kernel") if not gru else "gru_kernel"), "bound": "hbm",
+        "roofline": {"kernel": ("fbank_kernel + " if pcm_mode else "") + (({"tcn": "tcn_tc_kernel", "ds_tcn": "dstcn_tc_kernel"}.get(model_name, "mdtc_tc_kernel") if model.uses_tensor_cores(T) else "conv_backbone_kernel") if not gru else "gru_kernel"), "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src + ", burst", "traffic": traffic,
                      "algorithmic_bytes_per_frame": bpf, "launch_ms": launch_ms,

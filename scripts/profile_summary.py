@@ -37,6 +37,16 @@ def main():
                 i = hdr.index(w)
                 vals[w] = r[i]
                 print(f"  {w:95s} {r[i]:>16s} {units[i]}")
+        stalls = []
+        for i, n in enumerate(hdr):
+            if n.startswith("smsp__pcsamp_warps_issue_stalled_") and not n.endswith("_not_issued"):
+                try:
+                    stalls.append((float(r[i]), n[len("smsp__pcsamp_warps_issue_stalled_"):]))
+                except ValueError:
+                    pass
+        tot_s = sum(v for v, _ in stalls)
+        if tot_s > 0:
+            print("  warp-state samples (pc sampling):", ", ".join(f"{n} {100 * v / tot_s:.1f}%" for v, n in sorted(stalls, reverse=True) if v / tot_s >= 0.02))
         try:
             def tobytes(name):
                 i = hdr.index(name)

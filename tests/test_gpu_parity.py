@@ -223,13 +223,14 @@ def test_launch_counter_counts_our_kernels(native, models):
     assert native.launch_count() == n0 + 2
 
 
-@pytest.mark.parametrize("case", ["mdtc", "mdtc_cmvn_logits", "tcn"])
+@pytest.mark.parametrize("case", ["mdtc", "mdtc_cmvn_logits", "tcn", "ds_tcn"])
 def test_tensor_core_and_fp32_paths_agree(case, models):
-    """mdtc and dense tcn (hidden 64) run on tcgen05 (bf16x3) by default; the FP32-FMA kernel is the exact path."""
+    """mdtc, dense tcn (hidden 64) and ds_tcn (hidden 256) run on tcgen05 (bf16x3) by default; the FP32-FMA kernel
+    is the exact path."""
     cfg, m, sd, _ = models(case)
     B, T = 37, 40
     x = synth.features(B, T, 80, seed=5, cmvn_like=m.global_cmvn is not None).to(DEV)
-    cache = torch.randn(B, 64, m.backbone.padding, generator=torch.Generator().manual_seed(3)).to(DEV)
+    cache = torch.randn(B, m.hdim, m.backbone.padding, generator=torch.Generator().manual_seed(3)).to(DEV)
     try:
         m.precision = "fp32"
         y32, c32 = m(x, cache)

@@ -19,6 +19,7 @@
 #include "gru.h"
 #include "mdtc_tc.h"
 #include "tcn_tc.h"
+#include "dstcn_tc.h"
 
 namespace wekws {
 
@@ -96,6 +97,8 @@ struct wekws_model {
   TcArgs tcargs{};
   bool tcn_ok = false;                      // tensor-core path for the dense TCN (hidden 64)
   TcnTcArgs tcnargs{};
+  bool ds_ok = false;                       // tensor-core path for the depthwise-separable TCN (hidden 256)
+  DsTcArgs dsargs{};
 };
 
 namespace {
@@ -212,12 +215,49 @@ void write_w_image(uint8_t* dst, const std::vector<float>& wt /*[K][64]*/, int K
     }
 }
 
-// Tensor-core eligibility + pre-swizzled bf16x3 weight images (mdtc_tc.cu)
+// Same layout for 128 output channels n0 .. n0+127 of a [K][ldn] matrix: hi at dst, lo at dst + 16384 (dstcn_tc.cu)
+void write_w_image128(uint8_t* dst, const std::vector<float>& wt, int ldn, int K, int k0, int n0) {
+  memset(dst, 0, 32768);
+  for (int n = 0; n < 128; ++n)
+    for (int kk = 0; kk < 64 && k0 + kk < K; ++kk) {
+      const float w = wt[(size_t)(k0 + kk) * ldn + n0 + n];
+      const uint16_t hi = bf16_rn(w);
+      const uint16_t lo = bf16_rn(w - bf16_to_f(hi));
+      const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+      memcpy(dst + off, &hi, 2);
+      memcpy(dst + 16384 + off, &lo, 2);
+    }
+}
+
+// Tensor-core eligibility + pre-swizzled bf16x3 weight images (mdtc_tc.cu, tcn_tc.cu, dstcn_tc.cu)
 void pack_tc(wekws_model* m) {
   m->tc_ok = false;
   m->tcn_ok = false;
+  m->ds_ok = false;
   m->h_wimg.clear();
   const wekws_model_config& c = m->cfg;
+  if (c.backbone == WEKWS_BACKBONE_DSTCN) {
+    DsTcArgs& t = m->dsargs;
+    memset(&t, 0, sizeof(t));
+    const ConvArgs& a = m->conv;
+    t.idim = a.idim; t.odim = a.odim; t.nblocks = a.nblocks; t.ktaps = a.ktaps; t.P = a.P;
+    t.act = a.act; t.has_cmvn = a.has_cmvn;
+    t.v_mean = a.v_mean; t.v_istd = a.v_istd; t.v_bp = a.v_bp; t.v_blocks = a.v_blocks;
+    t.v_blk_stride = a.v_blk_stride; t.v_wc = a.v_wc; t.v_bc = a.v_bc;
+    for (int b = 0; b < a.nblocks; ++b) { t.dil[b] = a.dil[b]; t.coff[b] = a.coff[b]; }
+    if (!dstcn_tc_eligible(t, c.hdim)) return;
+    if (m->folded.size() != (size_t)(1 + a.nblocks)) return;
+    const int natoms = (a.idim + 63) / 64;
+    m->h_wimg.assign((size_t)(2 * natoms + 8 * a.nblocks) * 32768, 0);
+    uint8_t* dst = m->h_wimg.data();
+    for (int at = 0; at < natoms; ++at)
+      for (int h = 0; h < 2; ++h, dst += 32768) write_w_image128(dst, m->folded[0], 256, a.idim, 64 * at, 128 * h);
+    for (int b = 0; b < a.nblocks; ++b)
+      for (int ks = 0; ks < 4; ++ks)
+        for (int h = 0; h < 2; ++h, dst += 32768) write_w_image128(dst, m->folded[1 + b], 256, 256, 64 * ks, 128 * h);
+    m->ds_ok = true;
+    return;
+  }
   if (c.backbone == WEKWS_BACKBONE_TCN && c.hdim == 64) {
     TcnTcArgs& t = m->tcnargs;
     memset(&t, 0, sizeof(t));
@@ -470,11 +510,12 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
     WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_chunk_off, m->h_chunk_off.size() * sizeof(int)));
     WEKWS_CUDA_OK(cudaMemcpy(m->d_chunk_off, m->h_chunk_off.data(), m->h_chunk_off.size() * sizeof(int), cudaMemcpyHostToDevice));
     m->conv.wstream = m->d_stream; m->conv.chunk_off = m->d_chunk_off; m->conv.vec = m->d_vec;
-    if (m->tc_ok || m->tcn_ok) {
+    if (m->tc_ok || m->tcn_ok || m->ds_ok) {
       WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_wimg, m->h_wimg.size()));
       WEKWS_CUDA_OK(cudaMemcpy(m->d_wimg, m->h_wimg.data(), m->h_wimg.size(), cudaMemcpyHostToDevice));
       m->tcargs.wimg = m->d_wimg; m->tcargs.vec = m->d_vec;
       m->tcnargs.wimg = m->d_wimg; m->tcnargs.vec = m->d_vec;
+      m->dsargs.wimg = m->d_wimg; m->dsargs.vec = m->d_vec;
     }
     m->conv_max_T = conv_backbone_max_T(m->conv, m->padmax);
     WEKWS_REQUIRE(m->conv_max_T >= 1, "model does not fit the fused kernel's shared memory");
@@ -492,7 +533,7 @@ extern "C" int wekws_model_set_precision(wekws_model* m, int mode) {
 }
 
 extern "C" int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T) {
-  return (m && m->finalized && (m->tc_ok || m->tcn_ok) && m->precision == 0 && T >= 8) ? 1 : 0;
+  return (m && m->finalized && (m->tc_ok || m->tcn_ok || m->ds_ok) && m->precision == 0 && T >= 8) ? 1 : 0;
 }
 
 extern "C" int64_t wekws_model_packed_floats(const wekws_model* m, int which) {
@@ -534,7 +575,8 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
                         (d_in_cache == nullptr || ((uintptr_t)d_in_cache & 15) == 0) &&
                         ((uintptr_t)d_feats & 15) == 0 && ((uintptr_t)d_out_cache & 15) == 0;
     const bool use_tcn = m->tcn_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
-    const int maxT = use_tc ? tc_max_T() : use_tcn ? tcn_tc_max_T() : m->conv_max_T;
+    const bool use_ds = m->ds_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
+    const int maxT = use_tc ? tc_max_T() : use_tcn ? tcn_tc_max_T() : use_ds ? dstcn_tc_max_T() : m->conv_max_T;
     const int nchunk = (int)((T + maxT - 1) / maxT);
     const int Tc = (int)((T + nchunk - 1) / nchunk);
     for (int64_t t0 = 0; t0 < T; t0 += Tc) {
@@ -549,6 +591,20 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
         a.feat_bstride = T * m->cfg.idim;
         a.out_bstride = T * m->cfg.odim;
         int rc = mdtc_tc_launch(a, m->padmax, st);
+        if (rc) return rc;
+        continue;
+      }
+      if (use_ds) {
+        DsTcArgs a = m->dsargs;
+        a.feats = d_feats + t0 * m->cfg.idim;
+        a.out = d_out + t0 * m->cfg.odim;
+        a.in_cache = t0 == 0 ? d_in_cache : d_out_cache;
+        a.out_cache = d_out_cache;
+        a.B = (int)B;
+        a.T = (int)(T - t0 < Tc ? T - t0 : Tc);
+        a.feat_bstride = T * m->cfg.idim;
+        a.out_bstride = T * m->cfg.odim;
+        int rc = dstcn_tc_launch(a, st);
         if (rc) return rc;
         continue;
       }
