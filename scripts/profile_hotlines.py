@@ -36,7 +36,8 @@ for r in rows:
                 pass
 tot = sum(v["# Samples"] for v in agg.values()) or 1
 print(f"total samples {tot:.0f}")
-for key, v in sorted(agg.items(), key=lambda kv: -kv[1]["# Samples"])[:n]:
+keyf = (lambda kv: -kv[1]["Instructions Executed"]) if len(sys.argv) > 3 and sys.argv[3] == "inst" else (lambda kv: -kv[1]["# Samples"])
+for key, v in sorted(agg.items(), key=keyf)[:n]:
     st = sorted(((x, h[6:]) for h, x in v.items() if h.startswith("stall_") and x > 0), reverse=True)[:3]
     print(f"{100 * v['# Samples'] / tot:5.1f}%  {key[0]}:{key[1]:<4d} inst {v['Instructions Executed']:>9.0f}  " +
           ",".join(f"{h} {x:.0f}" for x, h in st) + f"   | {src[key]}")

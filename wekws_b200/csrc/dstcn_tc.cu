@@ -18,6 +18,8 @@
 // Warp roles: 16 compute warps (row = 32 * (warp % 4) + lane, channel group = warp / 4) + 1 issuer warp.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "dstcn_tc.h"
 #include "tc_common.cuh"
@@ -43,7 +45,7 @@ constexpr int TM_A = 256, TM_COLS = 512;
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 __device__ __forceinline__ float ld_global_f32(const float* p) {
   float v;
-  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 // predicated global load: 0 when pred == 0 (the address is then not dereferenced)
@@ -68,17 +70,20 @@ __device__ __forceinline__ void split_to_tmem(const float (&v)[8], uint32_t t_hi
   tmem_st4(t_lo, l);
 }
 
+// PP: compile-time cache row pitch (floats) so the cache loads get immediate offsets; 0 = read it from the arguments
+template <int PP>
 __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   __shared__ uint64_t mma_bar, coef_bar, a_rdy[2], ab_free[2], w_bar[NW], w_free[NW];
   __shared__ uint32_t tmem_slot;
+  __shared__ int store_ctr[1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer = warp == NCW;
   const int q = warp & 3, g = (warp >> 2) & 3;
   const int row = 32 * q + lane;
-  const int T = a.T;
+  const int T = a.T, P = PP ? PP : a.P;
   const float* vec = a.vec;
   float* X = reinterpret_cast<float*>(base + OFF_X);
   float* coef = reinterpret_cast<float*>(base + OFF_COEF);
@@ -122,8 +127,19 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
     bulk_g2s(Wring + slot * W_SLOT, a.wimg + (size_t)n * W_SLOT, W_SLOT, &w_bar[slot]);
     ++gl;
   };
-  if (is_issuer && lane == 0)
+  // the cache of the streams of a pass is pulled into L2 one pass ahead, so the depthwise taps that read it
+  // straight from global memory see L2 latency instead of HBM latency
+  auto prefetch_cache = [&](int first, int n) {
+    if (!a.prefetch_ok) return;
+    for (int i = 0; i < n; ++i)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.in_cache + (size_t)(first + i) * C * P),
+                   "r"(C * P * 4)
+                   : "memory");
+  };
+  if (is_issuer && lane == 0) {
     for (int i = 0; i < NW; ++i) load_next();
+    prefetch_cache(sb, min(spt, se - sb));
+  }
 
   while (done < se) {
     const int remaining = se - done;
@@ -163,6 +179,7 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
           bulk_g2s(coef, vec + a.v_blocks + (size_t)blk * a.v_blk_stride, COEF_FLOATS * 4, &coef_bar);
         };
         load_coef(0);
+        if (done < se) prefetch_cache(done, min(spt, se - done));
         // ---- first Linear
         {
           const int ks0 = (min(a.idim, 64) + 15) >> 4, ks1 = natoms > 1 ? (a.idim - 64 + 15) >> 4 : 0;
@@ -196,8 +213,12 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
       }
     } else {
       // ================================================================== COMPUTE WARPS
+      // Rows are ordered frame-major: row = t * ns + s, and X[c][row] likewise, so a tap is a column shift of
+      // j * d * ns and the rows of a warp span ~32 / ns consecutive frames: only the warps holding the first frames
+      // of the chunk reach back into the cache, and only for their first taps.
       const bool valid = row < rows, q_live = 32 * q < rows;
-      const int s = valid ? row / T : 0, t = valid ? row - s * T : 0;
+      const int t = valid ? row / ns : 0, s = valid ? row - t * ns : 0;
+      const int t_min = (32 * q) / ns;                 // first frame of this warp's rows
       const uint32_t tm_row = tmem + ((uint32_t)(32 * q) << 16);
 
       auto hand_over = [&](int b) {
@@ -245,11 +266,18 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
           float d[16];
           tmem_ld16(tm_row + c0, d);
           if (valid) {
+            const float4* bp4 = reinterpret_cast<const float4*>(vec + a.v_bp + c0);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) X[(c0 + e) * RPX + row] = fmaxf(d[e] + __ldg(vec + a.v_bp + c0 + e), 0.f);
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 bv = __ldg(bp4 + e4);
+              const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) X[(c0 + 4 * e4 + u) * RPX + row] = fmaxf(d[4 * e4 + u] + bb[u], 0.f);
+            }
           }
         }
       }
+      if (tid == 0) store_ctr[0] = 0;
       tc_fence_before();
       compute_barrier();
       wd_mark(3);
@@ -259,8 +287,54 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
         mbar_wait(&coef_bar, coef_par);
         coef_par ^= 1u;
         // taps that reach back before the chunk read cat index < pad from the cache row of this stream
-        const float* crow = valid && a.in_cache != nullptr ? a.in_cache + (size_t)(b0 + s) * C * a.P + off : nullptr;
-        const int t0 = valid ? t : -(1 << 20);         // padding rows: every tap takes the (absent) cache path -> 0
+        const float* crow = valid && a.in_cache != nullptr ? a.in_cache + (size_t)(b0 + s) * C * P + off : nullptr;
+        const int t0 = valid ? t : -(1 << 20);         // padding rows: every cache-capable tap takes the absent-cache path
+        // taps j < jc can need the cache for some row of this warp (t_min + j d < pad); rounded up to a compiled variant
+        const int jc = pad > t_min ? min(KT - 1, (pad - t_min + d - 1) / d) : 0;
+
+        // depthwise taps of 8 channels -> ReLU -> bf16 hi/lo -> TMEM operand buffer b.  Taps j < JC are compiled with
+        // a predicated global load (cache part) next to the shared load (frame part), the rest with the shared load
+        // only; everything is branch-free so the loads of a chunk are in flight together.
+        auto dw_chunk = [&](auto jct, int c0, uint32_t t_hi, uint32_t t_lo) {
+          constexpr int JC = decltype(jct)::value;
+          float acc[8];
+          {
+            const float4 b0v = *reinterpret_cast<const float4*>(coef + KT * C + c0);
+            const float4 b1v = *reinterpret_cast<const float4*>(coef + KT * C + c0 + 4);
+            acc[0] = b0v.x; acc[1] = b0v.y; acc[2] = b0v.z; acc[3] = b0v.w;
+            acc[4] = b1v.x; acc[5] = b1v.y; acc[6] = b1v.z; acc[7] = b1v.w;
+          }
+          const float* xc = X + c0 * RPX + row;
+          const float* gc = crow + (size_t)c0 * P + t0;
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(coef + j * C + c0);
+            const float4 w1 = *reinterpret_cast<const float4*>(coef + j * C + c0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const int sh = (j * d - pad) * ns;         // column shift of the frame part
+            float v[8];
+            if (j < JC) {
+              const bool in_c = t0 + j * d < pad, pg = in_c && crow != nullptr;
+              const float* xp = in_c ? X + c0 * RPX : xc + sh;
+              const float* gp = gc + j * d;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float vx = xp[u * RPX];
+                const float vg = pg ? ld_global_f32(gp + u * P) : 0.f;   // L1-cached: neighbouring taps/rows re-read it
+                v[u] = in_c ? vg : vx;
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = xc[sh + u * RPX];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = fmaf(w[u], v[u], acc[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = fmaxf(acc[u], 0.f);
+          split_to_tmem(acc, t_hi, t_lo);
+        };
+
         for (int ks = 0; ks < 4; ++ks) {
           const int b = ks & 1;
           wd_mark(10000 + blk * 10 + ks);
@@ -273,58 +347,45 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
               const int c0 = 64 * ks + 16 * g + 8 * half;
-              float acc[8];
-              {
-                const float4 b0v = *reinterpret_cast<const float4*>(coef + KT * C + c0);
-                const float4 b1v = *reinterpret_cast<const float4*>(coef + KT * C + c0 + 4);
-                acc[0] = b0v.x; acc[1] = b0v.y; acc[2] = b0v.z; acc[3] = b0v.w;
-                acc[4] = b1v.x; acc[5] = b1v.y; acc[6] = b1v.z; acc[7] = b1v.w;
-              }
-#pragma unroll
-              for (int j = 0; j < KT; ++j) {
-                const float4 w0 = *reinterpret_cast<const float4*>(coef + j * C + c0);
-                const float4 w1 = *reinterpret_cast<const float4*>(coef + j * C + c0 + 4);
-                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                const int idx = t0 + j * d;            // position in cat(cache, x)
-                const bool in_cache = idx < pad;
-                // branch-free: a predicated global load (cache part) and an always-valid shared load (frame part),
-                // so the 64 loads of a chunk can be in flight together
-                const float* gp = crow + (size_t)c0 * a.P + idx;
-                const float* xp = X + c0 * RPX + (in_cache ? 0 : row + j * d - pad);
-                const uint32_t pg = in_cache && crow != nullptr;
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const float vg = ld_global_f32_pred(gp + (size_t)u * a.P, pg);
-                  const float vx = xp[u * RPX];
-                  v[u] = in_cache ? vg : vx;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] = fmaf(w[u], v[u], acc[u]);
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) acc[u] = fmaxf(acc[u], 0.f);
-              split_to_tmem(acc, tm_row + TM_A + 64 * b + 4 * (2 * g + half), tm_row + TM_A + 32 + 64 * b + 4 * (2 * g + half));
+              const uint32_t t_hi = tm_row + TM_A + 64 * b + 4 * (2 * g + half), t_lo = t_hi + 32;
+              if (jc == 0) dw_chunk(std::integral_constant<int, 0>{}, c0, t_hi, t_lo);
+              else if (jc <= 3) dw_chunk(std::integral_constant<int, 3>{}, c0, t_hi, t_lo);
+              else if (jc <= 5) dw_chunk(std::integral_constant<int, 5>{}, c0, t_hi, t_lo);
+              else dw_chunk(std::integral_constant<int, 7>{}, c0, t_hi, t_lo);
             }
           }
           if (ks == 3) {
-            // New cache slices (tcn.py:54: last `pad` columns of cat(cache, x)).  Every warp is past its last read
-            // of the old slices after this barrier, so out_cache may alias in_cache; the stores precede this warp's
-            // last hand-over, hence the epilogue (which overwrites x) cannot start before all of them are issued.
-            compute_barrier();
-            for (int r = warp; r < ns * C; r += NCW) {
-              const int ss = r >> 8, c = r & (C - 1);
-              const size_t grow = ((size_t)(b0 + ss) * C + c) * a.P + off;
-              const float* xrow = X + c * RPX + ss * T;
-              for (int p0 = 0; p0 < pad; p0 += 32) {   // ascending: a row shifts left by T, reads stay ahead of writes
-                const int p = p0 + lane, i = T + p;
-                float v = 0.f;
-                if (p < pad) {
-                  if (i >= pad) v = xrow[i - pad];
-                  else if (a.in_cache != nullptr) v = ld_global_f32(a.in_cache + grow + i);
+            // New cache slices (tcn.py:54: last `pad` columns of cat(cache, x)), stored before this warp's last
+            // hand-over so the epilogue (which overwrites x) cannot start before every store has been issued.  x is
+            // stable during the whole depthwise phase, so a warp starts as soon as its own taps are done and takes
+            // row groups from a shared counter: the warps without cache taps finish early and do most of the moving.
+            // Only when out_cache aliases in_cache must every warp first be past its last read of the old slices.
+            if (a.aliased) compute_barrier();
+            const int L = pad <= 8 ? 8 : pad <= 16 ? 16 : 32, npr = 32 / L, sub = lane / L, pl = lane - sub * L;
+            const int ngroups = ns * C / npr;          // a group = npr rows of `pad` floats, one warp iteration per L floats
+            const size_t pbase = (size_t)b0 * C * P + off;
+            const float* ic = a.in_cache != nullptr ? a.in_cache + pbase : nullptr;
+            float* oc = a.out_cache + pbase;
+            const int from_cache = pad - T;            // elements p < pad - T come from the old slice (column p + T)
+            for (;;) {
+              int g0 = 0;
+              if (lane == 0) g0 = atomicAdd(store_ctr, 4);
+              g0 = __shfl_sync(0xffffffffu, g0, 0);
+              if (g0 >= ngroups) break;
+              const int g1 = min(g0 + 4, ngroups);
+              for (int gi = g0; gi < g1; ++gi) {
+                const int r = gi * npr + sub, ss = r >> 8, c = r & (C - 1), rp = r * P;
+                const float* xrow = X + c * RPX + ss + (T - pad) * ns;      // element p of the new slice = xrow[p * ns]
+                for (int p0 = 0; p0 < pad; p0 += L) {  // ascending: a row shifts left by T, reads stay ahead of writes
+                  const int p = p0 + pl;
+                  const bool act = p < pad, fx = p >= from_cache;
+                  const float xv = xrow[(act && fx ? p : pad - T) * ns];
+                  float v = 0.f;
+                  if (act && !fx && ic != nullptr) v = __ldcg(ic + rp + T + p);
+                  v = fx ? xv : v;
+                  if (a.aliased) __syncwarp();
+                  if (act) oc[rp + p] = v;
                 }
-                __syncwarp();
-                if (p < pad) a.out_cache[grow + p] = v;
               }
             }
           }
@@ -341,14 +402,21 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
             float dd[16];
             tmem_ld16(tm_row + c0, dd);
             if (valid) {
+              const float4* b4 = reinterpret_cast<const float4*>(bb + c0);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                float* xp = X + (c0 + e) * RPX + row;
-                *xp = fmaxf(dd[e] + __ldg(bb + c0 + e), 0.f) + *xp;
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 bv = __ldg(b4 + e4);
+                const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float* xp = X + (c0 + 4 * e4 + u) * RPX + row;
+                  *xp = fmaxf(dd[4 * e4 + u] + bq[u], 0.f) + *xp;
+                }
               }
             }
           }
         }
+        if (tid == 0) store_ctr[0] = 0;
         tc_fence_before();
         compute_barrier();
       }
@@ -373,7 +441,7 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
         float y = __ldg(vec + a.v_bc + j) + coef[(j * 4 + 0) * 128 + r] + coef[(j * 4 + 1) * 128 + r] +
                   coef[(j * 4 + 2) * 128 + r] + coef[(j * 4 + 3) * 128 + r];
         if (a.act == WEKWS_ACT_SIGMOID) y = sigmoidf_acc(y);
-        const int ss = r / T, tt = r - ss * T;
+        const int tt = r / ns, ss = r - tt * ns;
         a.out[(size_t)(b0 + ss) * a.out_bstride + (size_t)tt * odim + j] = y;
       }
     }
@@ -397,6 +465,14 @@ int dstcn_tc_max_T() { return RPX; }
 int dstcn_tc_launch(DsTcArgs a, cudaStream_t st) {
   WEKWS_REQUIRE(a.T >= 1 && a.T <= RPX && a.B >= 1, "dstcn_tc_launch: bad shape");
   a.spt = RPX / a.T;
+  a.prefetch_ok = a.in_cache != nullptr && ((uintptr_t)a.in_cache & 15) == 0 && (C * a.P * 4) % 16 == 0 &&
+                  getenv("WEKWS_DS_PREFETCH") != nullptr;      // measured: no gain on B200 (0.357 vs 0.351 ms), off by default
+  {
+    const size_t bytes = (size_t)a.B * C * a.P * sizeof(float);
+    const char* i0 = reinterpret_cast<const char*>(a.in_cache);
+    const char* o0 = reinterpret_cast<const char*>(a.out_cache);
+    a.aliased = a.in_cache != nullptr && i0 < o0 + bytes && o0 < i0 + bytes;
+  }
   const int sms = device_sm_count();
   const int tiles = (a.B + a.spt - 1) / a.spt;
   const int grid = tiles < sms ? tiles : sms;
@@ -404,10 +480,12 @@ int dstcn_tc_launch(DsTcArgs a, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    WEKWS_CUDA_OK(cudaFuncSetAttribute(dstcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    WEKWS_CUDA_OK(cudaFuncSetAttribute(dstcn_tc_kernel<105>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    WEKWS_CUDA_OK(cudaFuncSetAttribute(dstcn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set[dev] = true;
   }
-  dstcn_tc_kernel<<<grid, NT_TC, SMEM_TOTAL, st>>>(a);
+  if (a.P == 105) dstcn_tc_kernel<105><<<grid, NT_TC, SMEM_TOTAL, st>>>(a);     // ds_tcn.yaml: k = 8, dilations 1, 2, 4, 8
+  else dstcn_tc_kernel<0><<<grid, NT_TC, SMEM_TOTAL, st>>>(a);
   return check_launch("dstcn_tc_kernel");
 }
 

@@ -23,6 +23,8 @@ struct DsTcArgs {
   int dil[kMaxBlocks];
   int coff[kMaxBlocks];
   int spt;                 // streams per 128-row tile (set by dstcn_tc_launch)
+  int aliased;             // out_cache overlaps in_cache (set by dstcn_tc_launch)
+  int prefetch_ok;         // in_cache present and 16-byte aligned with 16-byte stream pitch (set by dstcn_tc_launch)
 };
 
 bool dstcn_tc_eligible(const DsTcArgs& a, int hdim);
