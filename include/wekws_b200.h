@@ -99,6 +99,16 @@ WEKWS_API void wekws_fbank_destroy(wekws_fbank* fb);
 WEKWS_API int64_t wekws_fbank_num_frames(const wekws_fbank* fb, int64_t num_samples);
 WEKWS_API int wekws_fbank_num_mel_bins(const wekws_fbank* fb);
 
+/* MFCC mode: the front-end of the shipped mdtc / mdtc_small configs
+ * (examples/hi_xiaowen/s0/conf/mdtc.yaml:8-14 `feature_type: mfcc`), i.e.
+ * torchaudio.compliance.kaldi.mfcc as called by wekws/dataset/processor.py:157-166 (compute_mfcc):
+ * the log-mel row times a DCT-II matrix h_dct[num_mel_bins][num_ceps] (ortho, first column sqrt(1/num_mel_bins)),
+ * times h_lifter[num_ceps] (NULL = no liftering), then the optional CMVN of wekws_fbank_forward over the
+ * num_ceps outputs.  After this call wekws_fbank_forward writes (B, max_frames, num_ceps).  num_ceps = 0
+ * switches back to log-mel output.  wekws_fbank_feature_dim = row width of the output in the current mode. */
+WEKWS_API int wekws_fbank_set_mfcc(wekws_fbank* fb, int num_ceps, const float* h_dct, const float* h_lifter);
+WEKWS_API int wekws_fbank_feature_dim(const wekws_fbank* fb);
+
 /* d_pcm: B waveforms, row b at d_pcm + b*pcm_stride elements, int16-scale values.
  * d_lens: optional per-waveform sample counts (NULL = all num_samples).
  * d_mean/d_istd: optional CMVN (NULL, NULL = none; istd NULL = mean only).

@@ -118,6 +118,37 @@ def fbank(waveform: Tensor, num_mel_bins: int = 80, frame_length: float = 25.0,
     return torch.max(e, torch.tensor(EPS, dtype=dtype)).log()             # :633
 
 
+def dct_matrix(num_ceps: int, num_mel_bins: int, dtype=torch.float32) -> Tensor:
+    """(num_mel_bins, num_ceps): torchaudio kaldi.py _get_dct_matrix = functional.create_dct(n, n, 'ortho')
+    with column 0 set to sqrt(1/n), first num_ceps columns."""
+    n = torch.arange(float(num_mel_bins), dtype=dtype)
+    k = torch.arange(float(num_mel_bins), dtype=dtype).unsqueeze(1)
+    dct = torch.cos(math.pi / float(num_mel_bins) * (n + 0.5) * k)
+    dct[0] *= 1.0 / math.sqrt(2.0)
+    dct *= math.sqrt(2.0 / float(num_mel_bins))
+    dct = dct.t().contiguous()
+    dct[:, 0] = math.sqrt(1 / float(num_mel_bins))
+    return dct[:, :num_ceps]
+
+
+def mfcc(waveform: Tensor, num_ceps: int = 80, num_mel_bins: int = 80, cepstral_lifter: float = 22.0,
+         frame_length: float = 25.0, frame_shift: float = 10.0, sample_frequency: float = 16000.0,
+         window_type: str = "povey", dtype=torch.float32) -> Tensor:
+    """Kaldi MFCC of one waveform with the arguments the reference passes (wekws/dataset/processor.py:157-166:
+    kaldi.mfcc(num_ceps, num_mel_bins, frame_length, frame_shift, dither=0, energy_floor=0, sample_frequency);
+    use_energy False, htk_compat False, subtract_mean False by default): log-mel fbank -> matmul with the DCT
+    matrix -> cepstral lifter (torchaudio kaldi.py mfcc body).  Returns (m, num_ceps)."""
+    assert num_ceps <= num_mel_bins
+    f = fbank(waveform, num_mel_bins, frame_length, frame_shift, sample_frequency, window_type, dtype=dtype)
+    if f.shape[0] == 0:
+        return torch.empty(0, num_ceps)
+    out = f.matmul(dct_matrix(num_ceps, num_mel_bins, dtype))
+    if cepstral_lifter != 0.0:
+        i = torch.arange(num_ceps)
+        out = out * (1.0 + 0.5 * cepstral_lifter * torch.sin(math.pi * i / cepstral_lifter)).to(dtype).unsqueeze(0)
+    return out
+
+
 # ---------------------------------------------------------------------------- CMVN
 def load_cmvn_json(path: str) -> Tuple[Tensor, Tensor]:
     """wekws/utils/cmvn.py:23-45, then the .float() of kws_model.py:104-108."""

@@ -103,6 +103,24 @@ def gen_fbank():
     print("fbank cases", len(waves))
 
 
+def gen_mfcc():
+    """kaldi.mfcc exactly as wekws/dataset/processor.py:157-166 calls it (the mdtc configs: num_ceps = num_mel_bins = 80)."""
+    import torchaudio.compliance.kaldi as kaldi
+    fb = np.load(os.path.join(OUT, "fbank.npz"))
+    arrays = {}
+    for name in ("gauss3000_a", "gauss3_short", "am_tone", "zeros", "one_frame", "chunk_0p3s_carry"):
+        w = torch.from_numpy(fb["wav_" + name])
+        for nc, nmel in ((80, 80), (40, 40), (13, 23)):
+            arrays[f"mfcc{nc}_{nmel}_{name}"] = kaldi.mfcc(
+                w.unsqueeze(0), num_ceps=nc, num_mel_bins=nmel, frame_length=25, frame_shift=10, dither=0.0,
+                energy_floor=0.0, sample_frequency=16000).numpy()
+    arrays["dct80"] = kaldi._get_dct_matrix(80, 80).numpy()
+    arrays["dct13_23"] = kaldi._get_dct_matrix(13, 23).numpy()
+    arrays["lifter80"] = kaldi._get_lifter_coeffs(80, 22.0).numpy()
+    np.savez_compressed(os.path.join(OUT, "mfcc.npz"), **arrays)
+    print("mfcc cases", len(arrays))
+
+
 def gen_cmvn():
     from wekws.utils.cmvn import load_cmvn
     path = synth.write_cmvn_json(80, seed=7)
@@ -128,6 +146,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_models()
     gen_fbank()
+    gen_mfcc()
     gen_cmvn()
     gen_init_parity()
     print("golden vectors written to", OUT)

@@ -173,6 +173,68 @@ def test_fbank_matches_reference_golden():
     assert torch.all(z == float(np.log(np.float32(O.EPS))))
 
 
+def _check_mfcc(out, ref, what, wav, nc, nmel):
+    """The reference's own fp32 MFCC sits 3.5e-3 max / 3.5e-4 mean from the float64 evaluation (sgemm over 80
+    log-mels of magnitude ~16); the kernel must agree with it to that order, or be at least as close to float64."""
+    assert out.shape == ref.shape, what
+    if not ref.size:
+        return
+    d = np.abs(out - ref)
+    if d.max() <= 6e-3 and d.mean() <= 6e-4:
+        return
+    truth = O.mfcc(wav, nc, nmel, dtype=torch.float64).numpy()
+    e_ref, e_out = np.abs(ref - truth), np.abs(out - truth)
+    assert e_out.max() <= max(6e-3, 1.5 * e_ref.max()), (what, e_out.max(), e_ref.max())
+    assert e_out.mean() <= max(6e-4, 1.5 * e_ref.mean()), (what, e_out.mean(), e_ref.mean())
+
+
+def test_mfcc_matches_reference_golden():
+    """kaldi.mfcc as processor.py:157-166 calls it; fused DCT + lifter epilogue of the Fbank kernel."""
+    from wekws_b200 import Mfcc, mfcc
+    g, fbg = golden("mfcc"), golden("fbank")
+    fes = {}
+    for k in [k for k in g.files if k.startswith("mfcc")]:
+        head, nmel, name = k.split("_", 2)
+        nc, nmel = int(head[4:]), int(nmel)
+        fe = fes.setdefault((nc, nmel), Mfcc(nc, nmel))
+        wav = torch.from_numpy(fbg["wav_" + name])
+        _check_mfcc(fe(wav.to(DEV)).cpu().numpy(), g[k], (k, "f32"), wav, nc, nmel)
+        _check_mfcc(fe(wav.to(torch.int16).to(DEV)).cpu().numpy(), g[k], (k, "s16"), wav, nc, nmel)
+    # the functional form with the reference's call signature, (1, N) -> (m, num_ceps)
+    wav = torch.from_numpy(fbg["wav_gauss3000_a"])
+    f = mfcc(wav.unsqueeze(0).to(DEV), num_ceps=80, num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0,
+             energy_floor=0.0, sample_frequency=16000)
+    _check_mfcc(f.cpu().numpy(), g["mfcc80_80_gauss3000_a"], "functional", wav, 80, 80)
+    assert Mfcc(80, 80)(torch.zeros(399, device=DEV)).shape == (0, 80)
+    with pytest.raises(AssertionError):
+        Mfcc(81, 80)
+
+
+def test_mfcc_batched_ragged_cmvn_and_model_pipeline(models):
+    from wekws_b200 import Mfcc
+    fe = Mfcc(80, 80)
+    pcm = synth.pcm_int16(5, 16000, seed=22)
+    lens = torch.tensor([16000, 15999, 8000, 400, 399], dtype=torch.int32)
+    mean, istd = torch.randn(80) * 3, torch.rand(80) * 0.2 + 0.05
+    out = fe(pcm.to(DEV), lengths=lens.to(DEV), mean=mean.to(DEV), istd=istd.to(DEV)).cpu()
+    assert out.shape == (5, 98, 80)
+    for b in range(5):
+        ref = O.mfcc(pcm[b, :lens[b]].float())
+        n = ref.shape[0]
+        if n:
+            d = (out[b, :n] - O.global_cmvn(ref, mean, istd)).abs()
+            assert d.max() <= 6e-3 and d.mean() <= 6e-4
+        assert float(out[b, n:].abs().max() if n < 98 else 0.0) == 0.0
+    # MFCC features into the model (the shipped mdtc recipe): posteriors against the oracle chain
+    cfg, m, sd, _ = models("mdtc_cmvn_logits")
+    y, _ = m(fe(pcm.to(DEV)))
+    ref_f = torch.stack([O.mfcc(pcm[b].float()) for b in range(5)])
+    y_ref, _ = O.kws_forward(sd, cfg, ref_f, None)
+    # the reference's own fp32-vs-float64 MFCC noise (3.5e-3) moves these logits (|y| ~ 13) by 4.5e-4 [measured with
+    # the oracle]; two fp32 implementations can differ by twice that, hence 3x the posterior gate for this chain
+    assert (y.cpu() - y_ref).abs().max() <= 3 * _tol(y_ref.numpy())
+
+
 def test_fbank_batched_ragged_cmvn_and_chunked_streaming():
     fb = Fbank(80)
     pcm = synth.pcm_int16(6, 16000, seed=21)

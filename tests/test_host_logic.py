@@ -28,6 +28,17 @@ def test_library_exports_every_declared_symbol(native):
     assert native.lib().wekws_abi_version() == native.ABI_VERSION
 
 
+def test_mfcc_constants_are_bit_identical_to_torchaudio():
+    """The DCT matrix and lifter the product uploads are built with torchaudio's own fp32 ops (goldens from
+    kaldi._get_dct_matrix / _get_lifter_coeffs, oracle/make_golden.py)."""
+    import numpy as np
+    from wekws_b200 import frontend
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mfcc.npz"))
+    assert np.array_equal(frontend.dct_matrix(80, 80).numpy(), g["dct80"])
+    assert np.array_equal(frontend.dct_matrix(13, 23).numpy(), g["dct13_23"])
+    assert np.array_equal(frontend.lifter_coeffs(80, 22.0).numpy(), g["lifter80"])
+
+
 def test_error_reporting_without_gpu(native):
     lib = native.lib()
     h = C.c_void_p()

@@ -60,6 +60,23 @@ def test_oracle_fbank_matches_reference_golden():
     assert np.all(z == np.float32(np.log(np.float32(O.EPS))))
 
 
+def test_oracle_mfcc_matches_reference_golden():
+    """kaldi.mfcc as wekws/dataset/processor.py:157-166 calls it (fixtures from oracle/make_golden.py gen_mfcc)."""
+    g, fb = golden("mfcc"), golden("fbank")
+    keys = [k for k in g.files if k.startswith("mfcc")]
+    assert len(keys) >= 18
+    for k in keys:
+        head, nmel, name = k.split("_", 2)
+        nc, nmel = int(head[4:]), int(nmel)
+        out = O.mfcc(torch.from_numpy(fb["wav_" + name]), nc, nmel).numpy()
+        assert out.shape == g[k].shape, k
+        # same ops as torchaudio (fbank -> matmul -> lifter); the matmul's summation order depends on the BLAS thread count
+        assert np.abs(out - g[k]).max() <= 2e-4, (k, np.abs(out - g[k]).max())
+    assert np.array_equal(O.dct_matrix(80, 80).numpy(), g["dct80"])
+    assert np.array_equal(O.dct_matrix(13, 23).numpy(), g["dct13_23"])
+    assert O.mfcc(torch.zeros(399)).shape == (0, 80)
+
+
 def test_oracle_cmvn_loader_matches_golden(tmp_path):
     p = synth.write_cmvn_json(80, seed=7, path=str(tmp_path / "cmvn.json"))
     mean, istd = O.load_cmvn_json(p)
@@ -84,6 +101,15 @@ def test_oracle_matches_live_reference(case):
             y_or, c_or = O.kws_forward(sd, cfg, x, c_or)
             assert (y_ref - y_or).abs().max() <= TOL_MODEL * max(1.0, float(y_ref.abs().max()))
             assert (c_ref - c_or).abs().max() <= 1e-5
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")
+def test_oracle_mfcc_matches_live_torchaudio():
+    import torchaudio.compliance.kaldi as kaldi
+    pcm = synth.pcm_int16(1, 16000 * 2, seed=78)[0].float()
+    ref = kaldi.mfcc(pcm.unsqueeze(0), num_ceps=80, num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0,
+                     energy_floor=0.0, sample_frequency=16000)
+    assert (O.mfcc(pcm) - ref).abs().max() <= 2e-4
 
 
 @pytest.mark.skipif(not have_reference(), reason="/root/reference not present (GPU box)")

@@ -3,15 +3,16 @@
 Public surface mirrors the reference (wenet-e2e/wekws):
     init_model, KWSModel     <- wekws/model/kws_model.py
     Fbank, fbank             <- torchaudio.compliance.kaldi.fbank as the reference calls it
+    Mfcc, mfcc               <- torchaudio.compliance.kaldi.mfcc  (processor.py:157-166, the mdtc configs' front-end)
     load_cmvn, load_kaldi_cmvn <- wekws/utils/cmvn.py
     patch_reference()        -> makes `wekws.model.kws_model` resolve to this implementation
 """
 from .cmvn import load_cmvn, load_kaldi_cmvn
 from .configs import MODEL_NAMES, model_config
-from .frontend import Fbank, fbank
+from .frontend import Fbank, Mfcc, fbank, mfcc
 from .kws_model import GlobalCMVN, KWSModel, init_model
 from .overlay import patch_reference
 
-__all__ = ["init_model", "KWSModel", "GlobalCMVN", "Fbank", "fbank", "load_cmvn", "load_kaldi_cmvn",
+__all__ = ["init_model", "KWSModel", "GlobalCMVN", "Fbank", "fbank", "Mfcc", "mfcc", "load_cmvn", "load_kaldi_cmvn",
            "model_config", "MODEL_NAMES", "patch_reference"]
 __version__ = "0.1.0"

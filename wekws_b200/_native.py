@@ -41,6 +41,8 @@ SIGNATURES = {
     "wekws_fbank_destroy": (None, [C.c_void_p]),
     "wekws_fbank_num_frames": (C.c_int64, [C.c_void_p, C.c_int64]),
     "wekws_fbank_num_mel_bins": (C.c_int, [C.c_void_p]),
+    "wekws_fbank_feature_dim": (C.c_int, [C.c_void_p]),
+    "wekws_fbank_set_mfcc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wekws_fbank_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wekws_model_create": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_void_p)]),

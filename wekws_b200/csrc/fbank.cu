@@ -50,6 +50,10 @@ struct FbankArgs {
   const int* moff;
   const float* mw;
   int mw_total;
+  // MFCC mode (nceps > 0): out = ((log-mel . dct) * lifter - mean) * istd, dct [nmel][nceps]
+  const float* dct;
+  const float* lifter;
+  int nceps, odim;          // odim = row width of `out` (nceps in MFCC mode, else nmel)
 };
 
 __device__ __forceinline__ int piA(int i) { return i + (i >> 5); }
@@ -82,7 +86,10 @@ __device__ __forceinline__ void dft8(float (&r)[8], float (&i)[8]) {
   r[3] = c3r + t7r; i[3] = c3i + t7i; r[7] = c3r - t7r; i[7] = c3i - t7i;
 }
 
-template <typename PCM>
+// MFCC = true adds the cepstral epilogue: the log-mel rows of the warp's FB_FPW frames stay in registers
+// (lane owns bins lane + 32 k) and are multiplied with the DCT matrix together, so every matrix element is
+// loaded once per FB_FPW frames and 12-16 accumulators run in parallel.
+template <typename PCM, bool MFCC>
 __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
   extern __shared__ __align__(16) float fb_smem[];
   float* s_stage = fb_smem;                                              // [STAGE]
@@ -130,13 +137,21 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
     }
     __syncthreads();
 
+    float lm[FB_FPW][4];                          // MFCC: log-mel rows of this warp's frames (0 for absent frames)
+    uint32_t fvalid = 0;
+    if (MFCC) {
+#pragma unroll
+      for (int ff = 0; ff < FB_FPW; ++ff)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lm[ff][k] = 0.f;
+    }
     for (int fi = 0; fi < FB_FPW; ++fi) {
     const int fl = warp + FB_WARPS * fi;          // frame of this warp within the item
     const long long f = f0 + fl;
     if (f >= a.max_frames) continue;          // warp-uniform; no block barrier inside this loop
-    float* outp = a.out + (b * a.max_frames + f) * a.nmel;
+    float* outp = a.out + (b * a.max_frames + f) * a.odim;
     if (f >= mb) {
-      for (int m = lane; m < a.nmel; m += 32) outp[m] = 0.f;
+      for (int m = lane; m < a.odim; m += 32) outp[m] = 0.f;
       continue;
     }
 
@@ -231,18 +246,79 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
     }
     __syncwarp();
     // ---- mel projection (sparse rows), log floor, CMVN ----
-    for (int m = lane; m < a.nmel; m += 32) {
-      const int st = __ldg(a.mstart + m), cnt = __ldg(a.mcnt + m);
-      const float* w = s_mw + __ldg(a.moff + m);
-      float e = 0.f;
-      for (int i = 0; i < cnt; ++i) e = fmaf(w[i], Br[st + i], e);
-      float v = logf(fmaxf(e, a.log_floor));
-      if (a.mean) v -= __ldg(a.mean + m);
-      if (a.istd) v *= __ldg(a.istd + m);
-      outp[m] = v;
+    if (!MFCC) {
+      for (int m = lane; m < a.nmel; m += 32) {
+        const int st = __ldg(a.mstart + m), cnt = __ldg(a.mcnt + m);
+        const float* w = s_mw + __ldg(a.moff + m);
+        float e = 0.f;
+        for (int i = 0; i < cnt; ++i) e = fmaf(w[i], Br[st + i], e);
+        float v = logf(fmaxf(e, a.log_floor));
+        if (a.mean) v -= __ldg(a.mean + m);
+        if (a.istd) v *= __ldg(a.istd + m);
+        outp[m] = v;
+      }
+    } else {
+      fvalid |= 1u << fi;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int m = lane + 32 * k;
+        if (m < a.nmel) {
+          const int st = __ldg(a.mstart + m), cnt = __ldg(a.mcnt + m);
+          const float* w = s_mw + __ldg(a.moff + m);
+          float e = 0.f;
+          for (int i = 0; i < cnt; ++i) e = fmaf(w[i], Br[st + i], e);
+          const float v = logf(fmaxf(e, a.log_floor));
+#pragma unroll
+          for (int ff = 0; ff < FB_FPW; ++ff)
+            if (fi == ff) lm[ff][k] = v;          // warp-uniform select keeps the row in registers
+        }
+      }
     }
     __syncwarp();
     }   // frames of this warp
+    // ---- MFCC: DCT-II (torchaudio kaldi.py mfcc: feature.matmul(dct_matrix)), lifter, CMVN ----
+    if (MFCC && fvalid != 0) {
+      float acc[FB_FPW][4];
+#pragma unroll
+      for (int ff = 0; ff < FB_FPW; ++ff)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) acc[ff][cc] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (32 * k < a.nmel) {
+          const int mend = min(32, a.nmel - 32 * k);
+#pragma unroll 4
+          for (int src = 0; src < mend; ++src) {
+            const float* drow = a.dct + (size_t)(32 * k + src) * a.nceps + lane;
+            float d[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) d[cc] = lane + 32 * cc < a.nceps ? __ldg(drow + 32 * cc) : 0.f;
+#pragma unroll
+            for (int ff = 0; ff < FB_FPW; ++ff) {
+              const float v = __shfl_sync(0xffffffffu, lm[ff][k], src);
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) acc[ff][cc] = fmaf(v, d[cc], acc[ff][cc]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int ff = 0; ff < FB_FPW; ++ff) {
+        if (!((fvalid >> ff) & 1u)) continue;
+        float* orow = a.out + (b * a.max_frames + f0 + warp + FB_WARPS * ff) * a.odim;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = lane + 32 * cc;
+          if (c < a.nceps) {
+            float v = acc[ff][cc];
+            if (a.lifter) v *= __ldg(a.lifter + c);
+            if (a.mean) v -= __ldg(a.mean + c);
+            if (a.istd) v *= __ldg(a.istd + c);
+            orow[c] = v;
+          }
+        }
+      }
+    }
   }
 }
 
@@ -264,6 +340,9 @@ struct wekws_fbank {
   int* d_moff = nullptr;
   float* d_mw = nullptr;
   int mw_total = 0;
+  int nceps = 0;            // > 0: MFCC mode (wekws_fbank_set_mfcc)
+  float* d_dct = nullptr;
+  float* d_lifter = nullptr;
 };
 
 extern "C" int wekws_fbank_create(const wekws_fbank_config* cfg, const float* h_window,
@@ -316,6 +395,7 @@ extern "C" void wekws_fbank_destroy(wekws_fbank* fb) {
   if (!fb) return;
   cudaFree(fb->d_tw256); cudaFree(fb->d_tw512); cudaFree(fb->d_window);
   cudaFree(fb->d_mstart); cudaFree(fb->d_mcnt); cudaFree(fb->d_moff); cudaFree(fb->d_mw);
+  cudaFree(fb->d_dct); cudaFree(fb->d_lifter);
   delete fb;
 }
 
@@ -325,6 +405,29 @@ extern "C" int64_t wekws_fbank_num_frames(const wekws_fbank* fb, int64_t num_sam
 }
 
 extern "C" int wekws_fbank_num_mel_bins(const wekws_fbank* fb) { return fb ? fb->cfg.num_mel_bins : 0; }
+
+extern "C" int wekws_fbank_feature_dim(const wekws_fbank* fb) {
+  return !fb ? 0 : fb->nceps > 0 ? fb->nceps : fb->cfg.num_mel_bins;
+}
+
+extern "C" int wekws_fbank_set_mfcc(wekws_fbank* fb, int num_ceps, const float* h_dct, const float* h_lifter) {
+  WEKWS_REQUIRE(fb, "wekws_fbank_set_mfcc: null handle");
+  cudaFree(fb->d_dct); cudaFree(fb->d_lifter);
+  fb->d_dct = nullptr; fb->d_lifter = nullptr; fb->nceps = 0;
+  if (num_ceps == 0) return WEKWS_OK;               // back to log-mel output
+  WEKWS_REQUIRE(h_dct, "wekws_fbank_set_mfcc: null dct matrix");
+  WEKWS_REQUIRE(num_ceps >= 1 && num_ceps <= fb->cfg.num_mel_bins, "mfcc: num_ceps %d must be in 1..num_mel_bins (%d)",
+                num_ceps, fb->cfg.num_mel_bins);   // torchaudio kaldi.py mfcc: assert num_ceps <= num_mel_bins
+  const size_t n = (size_t)fb->cfg.num_mel_bins * num_ceps;
+  WEKWS_CUDA_OK(cudaMalloc((void**)&fb->d_dct, n * sizeof(float)));
+  WEKWS_CUDA_OK(cudaMemcpy(fb->d_dct, h_dct, n * sizeof(float), cudaMemcpyHostToDevice));
+  if (h_lifter) {
+    WEKWS_CUDA_OK(cudaMalloc((void**)&fb->d_lifter, num_ceps * sizeof(float)));
+    WEKWS_CUDA_OK(cudaMemcpy(fb->d_lifter, h_lifter, num_ceps * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  fb->nceps = num_ceps;
+  return WEKWS_OK;
+}
 
 extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_dtype, int64_t B,
                                    int64_t num_samples, int64_t pcm_stride, const int32_t* d_lens,
@@ -346,26 +449,28 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.tw256 = fb->d_tw256; a.tw512 = fb->d_tw512; a.window = fb->d_window;
   a.mstart = fb->d_mstart; a.mcnt = fb->d_mcnt; a.moff = fb->d_moff; a.mw = fb->d_mw;
   a.mw_total = fb->mw_total;
+  a.dct = fb->d_dct; a.lifter = fb->d_lifter; a.nceps = fb->nceps;
+  a.odim = fb->nceps > 0 ? fb->nceps : fb->cfg.num_mel_bins;
   const long long items = B * ((max_frames + FB_FRAMES - 1) / FB_FRAMES);
   const size_t smem = (size_t)(STAGE + FB_WARPS * 2 * (A_SZ + B_SZ) + 2 * NBIN + WIN + 2 * NBIN + 64) * sizeof(float);
-  static int occ[2] = {0, 0};
-  const int ti = pcm_dtype == WEKWS_PCM_S16 ? 0 : 1;
+  static int occ[4] = {0, 0, 0, 0};
+  const bool mf = fb->nceps > 0;
+  const int ti = (pcm_dtype == WEKWS_PCM_S16 ? 0 : 1) + (mf ? 2 : 0);
+  const void* kern = ti == 0 ? (const void*)fbank_kernel<int16_t, false> : ti == 1 ? (const void*)fbank_kernel<float, false>
+                   : ti == 2 ? (const void*)fbank_kernel<int16_t, true> : (const void*)fbank_kernel<float, true>;
   if (occ[ti] == 0) {
-    if (ti == 0) {
-      WEKWS_CUDA_OK(cudaFuncSetAttribute(fbank_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      WEKWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[ti], fbank_kernel<int16_t>, FB_NT, smem));
-    } else {
-      WEKWS_CUDA_OK(cudaFuncSetAttribute(fbank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      WEKWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[ti], fbank_kernel<float>, FB_NT, smem));
-    }
+    WEKWS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WEKWS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[ti], kern, FB_NT, smem));
     if (occ[ti] < 1) occ[ti] = 1;
   }
   const long long cap = (long long)device_sm_count() * occ[ti];
   const int grid = (int)(items < cap ? items : cap);
   cudaStream_t st = (cudaStream_t)stream;
-  if (pcm_dtype == WEKWS_PCM_S16)
-    fbank_kernel<int16_t><<<grid, FB_NT, smem, st>>>(a);
-  else
-    fbank_kernel<float><<<grid, FB_NT, smem, st>>>(a);
+  switch (ti) {
+    case 0: fbank_kernel<int16_t, false><<<grid, FB_NT, smem, st>>>(a); break;
+    case 1: fbank_kernel<float, false><<<grid, FB_NT, smem, st>>>(a); break;
+    case 2: fbank_kernel<int16_t, true><<<grid, FB_NT, smem, st>>>(a); break;
+    default: fbank_kernel<float, true><<<grid, FB_NT, smem, st>>>(a); break;
+  }
   return check_launch("fbank_kernel");
 }

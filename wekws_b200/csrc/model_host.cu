@@ -650,8 +650,8 @@ extern "C" int wekws_pipeline_forward(wekws_fbank* fb, wekws_model* m, const voi
                                       float* d_feat_scratch, const float* d_in_cache, float* d_out,
                                       float* d_out_cache, uint32_t flags, void* stream) {
   WEKWS_REQUIRE(fb && m && d_feat_scratch, "wekws_pipeline_forward: null argument");
-  WEKWS_REQUIRE(wekws_fbank_num_mel_bins(fb) == m->cfg.idim, "pipeline: fbank has %d mel bins but the model expects input_dim %d",
-                wekws_fbank_num_mel_bins(fb), m->cfg.idim);
+  WEKWS_REQUIRE(wekws_fbank_feature_dim(fb) == m->cfg.idim, "pipeline: the front-end produces %d features but the model expects input_dim %d",
+                wekws_fbank_feature_dim(fb), m->cfg.idim);
   const int64_t frames = wekws_fbank_num_frames(fb, num_samples);
   int rc = wekws_fbank_forward(fb, d_pcm, pcm_dtype, B, num_samples, pcm_stride, nullptr, nullptr, nullptr,
                                d_feat_scratch, frames, stream);

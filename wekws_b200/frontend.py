@@ -54,6 +54,25 @@ def mel_filterbank(num_bins: int, n_fft: int, sample_freq: float, low_freq: floa
     return torch.max(torch.zeros(1), torch.min(up, down)).contiguous()
 
 
+def dct_matrix(num_ceps: int, num_mel_bins: int) -> torch.Tensor:
+    """(num_mel_bins, num_ceps) DCT-II matrix of torchaudio kaldi.py `_get_dct_matrix`: ortho-normalised
+    create_dct(n, n, 'ortho') with the first column replaced by sqrt(1/n), truncated to num_ceps columns."""
+    n = torch.arange(float(num_mel_bins))
+    k = torch.arange(float(num_mel_bins)).unsqueeze(1)
+    dct = torch.cos(math.pi / float(num_mel_bins) * (n + 0.5) * k)      # (n_mfcc, n_mels)
+    dct[0] *= 1.0 / math.sqrt(2.0)
+    dct *= math.sqrt(2.0 / float(num_mel_bins))
+    dct = dct.t().contiguous()
+    dct[:, 0] = math.sqrt(1 / float(num_mel_bins))
+    return dct[:, :num_ceps].contiguous()
+
+
+def lifter_coeffs(num_ceps: int, cepstral_lifter: float) -> torch.Tensor:
+    """torchaudio kaldi.py `_get_lifter_coeffs`: 1 + 0.5 Q sin(pi i / Q)."""
+    i = torch.arange(num_ceps)
+    return 1.0 + 0.5 * cepstral_lifter * torch.sin(math.pi * i / cepstral_lifter)
+
+
 class Fbank:
     """Batched GPU Fbank(+CMVN).  ``__call__(pcm)``: pcm (B, N) or (N,) int16 / float32 CUDA
     tensor in int16 scale (the reference multiplies normalised audio by 1<<15 first,
@@ -73,6 +92,10 @@ class Fbank:
         self.mel = mel_filterbank(num_mel_bins, self.n_fft, sample_frequency, low_freq, high_freq)
         self._handles = {}
         self.device = device
+        self.feature_dim = num_mel_bins          # row width of the output (num_ceps for the Mfcc subclass)
+
+    def _configure(self, handle) -> None:
+        """Hook for subclasses: extra native configuration of a freshly created handle."""
 
     def num_frames(self, num_samples: int) -> int:
         return 0 if num_samples < self.win else 1 + (num_samples - self.win) // self.shift
@@ -85,6 +108,7 @@ class Fbank:
                 _native.check(_native.lib().wekws_fbank_create(
                     C.byref(self.cfg), C.c_void_p(self.window.data_ptr()), C.c_void_p(self.mel.data_ptr()),
                     C.byref(h)), "wekws_fbank_create")
+                self._configure(h)
             self._handles[dev] = h
         return h
 
@@ -117,9 +141,9 @@ class Fbank:
         B, N = pcm.shape
         m = self.num_frames(N)
         if out is None:
-            out = torch.empty(B, m, self.num_mel_bins, device=dev, dtype=torch.float32)
-        elif tuple(out.shape) != (B, m, self.num_mel_bins) or not out.is_contiguous():
-            raise ValueError("out must be a contiguous (B, m, num_mel_bins) tensor")
+            out = torch.empty(B, m, self.feature_dim, device=dev, dtype=torch.float32)
+        elif tuple(out.shape) != (B, m, self.feature_dim) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous (B, m, feature_dim) tensor")
 
         def ptr(t, dt):
             if t is None:
@@ -141,6 +165,28 @@ class Fbank:
         return out[0] if squeeze else out
 
 
+class Mfcc(Fbank):
+    """Batched GPU MFCC(+CMVN): the Fbank kernel with a fused DCT-II + lifter epilogue.  Mirrors
+    ``kaldi.mfcc(waveform, num_ceps=..., num_mel_bins=..., frame_length=25, frame_shift=10, dither=0.0,
+    energy_floor=0.0, sample_frequency=...)`` (wekws/dataset/processor.py:157-166; the front-end of the shipped
+    mdtc configs, examples/hi_xiaowen/s0/conf/mdtc.yaml:8-14) -> (B, m, num_ceps).  mean / istd passed to
+    ``__call__`` are applied to the cepstra."""
+
+    def __init__(self, num_ceps: int = 80, num_mel_bins: int = 80, cepstral_lifter: float = 22.0, **kw):
+        if num_ceps > num_mel_bins:
+            raise AssertionError("num_ceps cannot be larger than num_mel_bins: %d vs %d" % (num_ceps, num_mel_bins))
+        super().__init__(num_mel_bins, **kw)
+        self.num_ceps = num_ceps
+        self.feature_dim = num_ceps
+        self.dct = dct_matrix(num_ceps, num_mel_bins)
+        self.lifter = lifter_coeffs(num_ceps, cepstral_lifter).float().contiguous() if cepstral_lifter != 0.0 else None
+
+    def _configure(self, handle) -> None:
+        _native.check(_native.lib().wekws_fbank_set_mfcc(
+            handle, self.num_ceps, C.c_void_p(self.dct.data_ptr()),
+            C.c_void_p(self.lifter.data_ptr()) if self.lifter is not None else None), "wekws_fbank_set_mfcc")
+
+
 _DEFAULT = {}
 
 
@@ -159,3 +205,21 @@ def fbank(waveform: torch.Tensor, num_mel_bins: int = 23, frame_length: float = 
         assert waveform.size(0) == 1, "kaldi.fbank expects a mono (1, N) waveform"
         return fb(waveform)[0]
     return fb(waveform)
+
+
+def mfcc(waveform: torch.Tensor, num_ceps: int = 13, num_mel_bins: int = 23, frame_length: float = 25.0,
+         frame_shift: float = 10.0, dither: float = 0.0, energy_floor: float = 0.0,
+         sample_frequency: float = 16000.0, cepstral_lifter: float = 22.0, window_type: str = "povey") -> torch.Tensor:
+    """Signature-compatible subset of torchaudio.compliance.kaldi.mfcc for the reference's call site
+    (processor.py:157-166): waveform (1, N) -> (m, num_ceps).  dither must be 0 (test-time setting)."""
+    if dither != 0.0:
+        raise NotImplementedError("wekws_b200.mfcc: dither is a training-time augmentation; use dither=0.0")
+    key = ("mfcc", num_ceps, num_mel_bins, frame_length, frame_shift, sample_frequency, cepstral_lifter, window_type)
+    fe = _DEFAULT.get(key)
+    if fe is None:
+        fe = _DEFAULT[key] = Mfcc(num_ceps, num_mel_bins, cepstral_lifter, frame_length=frame_length,
+                                  frame_shift=frame_shift, sample_frequency=sample_frequency, window_type=window_type)
+    if waveform.dim() == 2:
+        assert waveform.size(0) == 1, "kaldi.mfcc expects a mono (1, N) waveform"
+        return fe(waveform)[0]
+    return fe(waveform)
