@@ -2,13 +2,15 @@
 and against the CPU oracle.  Tolerances: posteriors <= 1e-4 max-abs (north_star); caches <= 1e-4
 scaled by magnitude; log-mel features <= 1e-3 max-abs / 1e-5 mean-abs (the oracle's own
 fp32-vs-fp64 noise floor is 9e-5..4.3e-4)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import kws_oracle as O
 from tests.cases import CASE_NAMES, CHUNKS, build_model
-from tests.conftest import golden
+from tests.conftest import ROOT, golden
 from wekws_b200 import Fbank, init_model, model_config, synth
 
 pytestmark = pytest.mark.gpu
@@ -273,6 +275,41 @@ def test_pcm_to_posterior_pipeline_matches_oracle(models):
     y_ref, c_ref = O.kws_forward(sd, cfg, ref_f, None)
     assert (y.cpu() - y_ref).abs().max() <= _tol(y_ref.numpy())
     assert (c.cpu() - c_ref).abs().max() <= 2e-3 * max(1.0, float(c_ref.abs().max()))
+
+
+@pytest.mark.parametrize("case,batch", [("mdtc", 40), ("ds_tcn", 17), ("gru", 1)])
+def test_native_runtime_shim_streams_like_the_python_model(case, batch, models, tmp_path):
+    """wekws::KeywordSpotting (C++ over the C ABI, no Python/ONNX) fed batch by batch as kws_main.cc:43-61 does ==
+    KWSModel streamed with the same chunking; Reset() starts a new stream."""
+    import subprocess
+    from wekws_b200 import export_native
+    cfg, m, sd, _ = models(case)
+    export_native(m, str(tmp_path / "m.wkb"))
+    T = 100
+    x = synth.features(1, T, 80, seed=9, cmvn_like=m.global_cmvn is not None)
+    x[0].numpy().tofile(str(tmp_path / "feats.f32"))
+    exe = os.path.join(ROOT, "wekws_b200", "runtime", "kws_main_b200")
+    reset_every = 3
+    r = subprocess.run([exe, str(tmp_path / "m.wkb"), str(tmp_path / "feats.f32"), "80", str(batch), str(reset_every)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert f"cache_dim: {m.hdim}" in r.stdout
+    rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("frame ")]
+    assert [int(p[1]) for p in rows] == list(range(T))
+    got = torch.tensor([[float(v) for v in p[3:]] for p in rows])
+    gru = case == "gru"
+    ref, cache, nb = [], None, 0
+    for s0 in range(0, T, batch):
+        if cache is None:
+            cache = torch.zeros(cfg["backbone"]["num_layers"], 1, cfg["hidden_dim"], device=DEV) if gru else torch.zeros(0, 0, 0)
+        y, cache = m(x[:, s0:s0 + batch].to(DEV), cache)
+        ref.append(y[0].cpu())
+        nb += 1
+        if nb % reset_every == 0:
+            cache = None
+    ref = torch.cat(ref)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= 2e-6          # same kernels, same chunking: only the 9-digit text round trip
 
 
 def test_launch_counter_counts_our_kernels(native, models):

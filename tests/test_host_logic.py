@@ -39,6 +39,30 @@ def test_mfcc_constants_are_bit_identical_to_torchaudio():
     assert np.array_equal(frontend.lifter_coeffs(80, 22.0).numpy(), g["lifter80"])
 
 
+def test_native_export_roundtrip_and_runtime_shim_symbols(tmp_path):
+    """.wkb exporter (the export_onnx.py role) and the C++ shim's link surface: wekws::KeywordSpotting with the
+    reference's public members (runtime/core/kws/keyword_spotting.h:26-55)."""
+    import subprocess
+    import torch
+    from wekws_b200 import export_native, init_model, model_config, synth
+    from wekws_b200.export import read_native
+    m = synth.randomize_(init_model(model_config("mdtc"))).eval()
+    meta = export_native(m, str(tmp_path / "m.wkb"))
+    assert meta["cache_dim"] == 64 and meta["cache_len"] == 244
+    fields, tensors = read_native(str(tmp_path / "m.wkb"))
+    assert fields[:4] == (0, 80, 64, 1)
+    sd = {k: v for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked")}
+    assert set(tensors) == set(sd)
+    assert all(torch.equal(tensors[k].reshape(-1), sd[k].float().reshape(-1)) for k in sd)
+    so = os.path.join(ROOT, "wekws_b200", "runtime", "libwekws_b200_runtime.so")
+    assert os.path.exists(so), "run __graft_entry__.build() first"
+    syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
+    for want in ("wekws::KeywordSpotting::KeywordSpotting(std::", "wekws::KeywordSpotting::Reset()",
+                 "wekws::KeywordSpotting::Forward(std::vector<std::vector<float"):
+        assert want in syms, want
+    assert os.access(os.path.join(ROOT, "wekws_b200", "runtime", "kws_main_b200"), os.X_OK)
+
+
 def test_error_reporting_without_gpu(native):
     lib = native.lib()
     h = C.c_void_p()

@@ -6,13 +6,15 @@ Public surface mirrors the reference (wenet-e2e/wekws):
     Mfcc, mfcc               <- torchaudio.compliance.kaldi.mfcc  (processor.py:157-166, the mdtc configs' front-end)
     load_cmvn, load_kaldi_cmvn <- wekws/utils/cmvn.py
     patch_reference()        -> makes `wekws.model.kws_model` resolve to this implementation
+    export_native()          -> weight file for the C++ runtime shim (the role of wekws/bin/export_onnx.py)
 """
 from .cmvn import load_cmvn, load_kaldi_cmvn
 from .configs import MODEL_NAMES, model_config
 from .frontend import Fbank, Mfcc, fbank, mfcc
 from .kws_model import GlobalCMVN, KWSModel, init_model
+from .export import export_native
 from .overlay import patch_reference
 
 __all__ = ["init_model", "KWSModel", "GlobalCMVN", "Fbank", "fbank", "Mfcc", "mfcc", "load_cmvn", "load_kaldi_cmvn",
-           "model_config", "MODEL_NAMES", "patch_reference"]
+           "model_config", "MODEL_NAMES", "patch_reference", "export_native"]
 __version__ = "0.1.0"
