@@ -149,7 +149,8 @@ WEKWS_API int wekws_model_pack(wekws_model* m);
 WEKWS_API int wekws_model_finalize(wekws_model* m);
 /* Arithmetic of the dense GEMMs: 0 = auto (default): tcgen05 tensor cores with a 3-pass bf16
  * operand split (~2^-17 relative, posteriors within 1e-5 of fp32) where a fused tensor-core
- * kernel exists (mdtc, hidden 64, chunk >= 8 frames), FP32 FMA elsewhere; 1 = FP32 FMA only. */
+ * kernel exists (mdtc / dense tcn with hidden 64, ds_tcn with hidden 256 and k = 8; chunk >= 8 frames),
+ * FP32 FMA elsewhere; 1 = FP32 FMA only. */
 WEKWS_API int wekws_model_set_precision(wekws_model* m, int mode);
 /* 1 if a forward with T frames per call runs the tcgen05 kernel (after finalize), else 0.    */
 WEKWS_API int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T);
@@ -163,6 +164,17 @@ WEKWS_API int wekws_model_packed_copy(const wekws_model* m, int which, float* h_
 WEKWS_API int wekws_model_forward(wekws_model* m, const float* d_feats, const float* d_in_cache,
                         float* d_out, float* d_out_cache, int64_t B, int64_t T,
                         uint32_t flags, void* stream);
+
+/* Detection statistics of max-pooling keyword models on the device, bit-exact with the host
+ * pipeline wekws/bin/score.py:128-137 ('{:.6f}' score file) -> wekws/bin/compute_det.py:76-105:
+ *   d_max_score[b,k]   = max over the first lens[b] frames of the text-rounded posterior (false-reject test),
+ *   d_triggers[b,k,i]  = triggers of the left-to-right scan "score >= thresholds[i] -> count, skip window_shift
+ *                        frames" (false alarms).
+ * d_post (B,T,K) posteriors; d_lens NULL = all T frames; d_thresholds nthr doubles (the host accumulates
+ * threshold += step exactly as the reference does).                                                   */
+WEKWS_API int wekws_det_stats(const float* d_post, const int32_t* d_lens, int64_t B, int64_t T, int K,
+                    const double* d_thresholds, int nthr, int window_shift, float* d_max_score,
+                    int32_t* d_triggers, void* stream);
 
 /* Raw PCM -> posteriors: Fbank(+CMVN from the model's global_cmvn.* if set) -> model.
  * d_feat_scratch: (B, frames, idim) floats of workspace owned by the caller.        */

@@ -314,3 +314,35 @@ def kws_forward(sd: Dict[str, Tensor], cfg: dict, feats: Tensor,
     if softmax:
         x = x.softmax(2)
     return x, new_cache
+
+
+# ---------------------------------------------------------------------------- detection statistics
+def det_stats(post: Tensor, lengths, step: float = 0.01, window_shift: int = 50):
+    """Pure-Python restatement of wekws/bin/score.py:128-137 (scores written as '{:.6f}') followed by
+    wekws/bin/compute_det.py:76-105 (threshold sweep; triggers counted left to right with a window_shift skip).
+    post (B, T, K).  Returns (thresholds list, max_score [B][K], triggers [B][K][n])."""
+    B, T, K = post.shape
+    thresholds, threshold = [], 0.0
+    while threshold <= 1.0:                                   # compute_det.py:79-105
+        thresholds.append(threshold)
+        threshold += step
+    max_score = [[None] * K for _ in range(B)]
+    triggers = [[None] * K for _ in range(B)]
+    for b in range(B):
+        n = T if lengths is None else int(lengths[b])
+        for k in range(K):
+            text = ' '.join(['{:.6f}'.format(x) for x in post[b, :n, k].tolist()])      # score.py:133-135
+            score_list = list(map(float, text.split()))                                 # compute_det.py:30
+            max_score[b][k] = max(score_list) if score_list else float('-inf')         # :83
+            row = []
+            for th in thresholds:
+                count, i = 0, 0
+                while i < len(score_list):                                              # :91-97
+                    if score_list[i] >= th:
+                        count += 1
+                        i += window_shift
+                    else:
+                        i += 1
+                row.append(count)
+            triggers[b][k] = row
+    return thresholds, max_score, triggers

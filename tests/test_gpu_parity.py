@@ -312,6 +312,34 @@ def test_native_runtime_shim_streams_like_the_python_model(case, batch, models, 
     assert (got - ref).abs().max() <= 2e-6          # same kernels, same chunking: only the 9-digit text round trip
 
 
+def test_det_stats_bit_exact_with_score_file_pipeline():
+    """the compute_det.py threshold sweep on the device == the host pipeline through the '{:.6f}' score
+    file, integer counts and rounded maxima bit for bit (oracle: oracle/kws_oracle.py det_stats)."""
+    from wekws_b200 import det_curve, det_stats
+    g = torch.Generator().manual_seed(11)
+    B, T, K = 7, 230, 2
+    post = torch.sigmoid(torch.randn(B, T, K, generator=g) * 3)
+    post[0, :5, 0] = torch.tensor([0.5, 0.4999995, 0.5000005, 0.01, 1.0])     # text-rounding ties and exact thresholds
+    post[1] = 0.0
+    lens = torch.tensor([230, 229, 100, 51, 1, 0, 230], dtype=torch.int32)
+    for ws in (50, 1, 7):
+        thr, ms, tr = det_stats(post.to(DEV), lens.to(DEV), step=0.01, window_shift=ws)
+        o_thr, o_ms, o_tr = O.det_stats(post, lens, 0.01, ws)
+        assert thr.tolist() == o_thr and len(o_thr) in (100, 101)
+        assert tr.cpu().tolist() == o_tr, ws
+        got = ms.cpu().double()
+        for b in range(B):
+            for k in range(K):
+                want = o_ms[b][k]
+                assert (got[b, k].item() == float(torch.tensor(want, dtype=torch.float32))) or (want == float("-inf") and got[b, k].item() == want)
+    thr, ms, tr = det_stats(post.to(DEV), None, window_shift=50)
+    assert tr.cpu().tolist() == O.det_stats(post, None, 0.01, 50)[2]
+    rows = det_curve(thr, ms, tr, [True, False, True, False, False, False, True], filler_hours=0.5)
+    assert len(rows) == thr.numel() and rows[0][2] == 0.0 and rows[-1][1] >= 0.0
+    with pytest.raises(RuntimeError):
+        det_stats(post)
+
+
 def test_launch_counter_counts_our_kernels(native, models):
     cfg, m, sd, _ = models("mdtc")
     x = synth.features(2, 40, 80, seed=1).to(DEV)
