@@ -312,6 +312,35 @@ def test_native_runtime_shim_streams_like_the_python_model(case, batch, models, 
     assert (got - ref).abs().max() <= 2e-6          # same kernels, same chunking: only the 9-digit text round trip
 
 
+def test_native_runtime_pcm_to_posterior_like_kws_main(models, tmp_path):
+    """The whole kws_main.cc flow in C++: int16 PCM -> wenet::FeaturePipeline (GPU Fbank, Hamming window as the
+    runtime uses, fed in 0.3 s chunks from a producer thread) -> wekws::KeywordSpotting, against the Python chain."""
+    import subprocess
+    from wekws_b200 import export_native
+    cfg, m, sd, _ = models("mdtc")
+    export_native(m, str(tmp_path / "m.wkb"))
+    pcm = synth.pcm_int16(1, 16000 * 2 + 123, seed=13)[0]
+    pcm.numpy().astype("<i2").tofile(str(tmp_path / "a.s16"))
+    exe = os.path.join(ROOT, "wekws_b200", "runtime", "kws_main_b200")
+    batch = 32
+    r = subprocess.run([exe, "--pcm", str(tmp_path / "m.wkb"), str(tmp_path / "a.s16"), "80", str(batch), "4800"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("frame ")]
+    got = torch.tensor([[float(v) for v in p[3:]] for p in rows])
+    feats = Fbank(80, window_type="hamming")(pcm.to(DEV)).unsqueeze(0)
+    T = feats.shape[1]
+    assert T == 1 + (pcm.numel() - 400) // 160 and [int(p[1]) for p in rows] == list(range(T))
+    ref, cache = [], torch.zeros(0, 0, 0)
+    for s0 in range(0, T, batch):
+        y, cache = m(feats[:, s0:s0 + batch], cache)
+        ref.append(y[0].cpu())
+    ref = torch.cat(ref)
+    # the C++ window / mel tables are built in double, the Python ones with torch fp32 ops: the features differ in
+    # the last bits and the posteriors by 2.4e-5 (measured) -- the posterior gate applies
+    assert (got - ref).abs().max() <= TOL_POST
+
+
 def test_det_stats_bit_exact_with_score_file_pipeline():
     """the compute_det.py threshold sweep on the device == the host pipeline through the '{:.6f}' score
     file, integer counts and rounded maxima bit for bit (oracle: oracle/kws_oracle.py det_stats)."""

@@ -58,7 +58,11 @@ def test_native_export_roundtrip_and_runtime_shim_symbols(tmp_path):
     assert os.path.exists(so), "run __graft_entry__.build() first"
     syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
     for want in ("wekws::KeywordSpotting::KeywordSpotting(std::", "wekws::KeywordSpotting::Reset()",
-                 "wekws::KeywordSpotting::Forward(std::vector<std::vector<float"):
+                 "wekws::KeywordSpotting::Forward(std::vector<std::vector<float",
+                 "wenet::FeaturePipeline::FeaturePipeline(wenet::FeaturePipelineConfig const&)",
+                 "wenet::FeaturePipeline::AcceptWaveform(std::vector<short", "wenet::FeaturePipeline::AcceptWaveform(std::vector<float",
+                 "wenet::FeaturePipeline::Read(int, std::vector<std::vector<float", "wenet::FeaturePipeline::set_input_finished()",
+                 "wenet::FeaturePipeline::ReadOne(std::vector<float", "wenet::FeaturePipeline::Reset()"):
         assert want in syms, want
     assert os.access(os.path.join(ROOT, "wekws_b200", "runtime", "kws_main_b200"), os.X_OK)
 
