@@ -18,15 +18,11 @@ struct wekws_fbank;
 
 namespace wenet {
 
+// 25 ms windows every 10 ms, as the reference derives them from the sample rate.
 struct FeaturePipelineConfig {
-  int num_bins;
-  int sample_rate;
-  int frame_length;
-  int frame_shift;
-  FeaturePipelineConfig(int num_bins, int sample_rate) : num_bins(num_bins), sample_rate(sample_rate) {
-    frame_length = sample_rate / 1000 * 25;  // 25 ms
-    frame_shift = sample_rate / 1000 * 10;   // 10 ms
-  }
+  int num_bins, sample_rate, frame_length, frame_shift;
+  FeaturePipelineConfig(int bins, int rate)
+      : num_bins(bins), sample_rate(rate), frame_length(rate / 1000 * 25), frame_shift(rate / 1000 * 10) {}
   void Info() const;
 };
 
@@ -37,41 +33,39 @@ class FeaturePipeline {
   FeaturePipeline(const FeaturePipeline&) = delete;
   FeaturePipeline& operator=(const FeaturePipeline&) = delete;
 
-  // The feature extraction is done in AcceptWaveform(); samples in int16 range.
+  // Producer side.  Samples are in int16 range; every complete frame of (carry + wav) is turned into a feature
+  // row on the GPU before the call returns, the tail that the next frame still needs is carried over.
   void AcceptWaveform(const std::vector<float>& wav);
   void AcceptWaveform(const std::vector<int16_t>& wav);
+  void set_input_finished();                       // end of audio: wakes a blocked reader; no AcceptWaveform after it
 
-  int num_frames() const { return num_frames_; }
+  // Consumer side (both block while the queue is empty and the input is still open).
+  bool ReadOne(std::vector<float>* feat);          // false <=> input finished and queue drained
+  bool Read(int num_frames, std::vector<std::vector<float>>* feats);   // false <=> stream ended before num_frames rows
+
+  void Reset();                                    // new utterance: drops queue, carry and counters
+  int num_frames() const { return num_frames_; }   // rows produced so far
   int feature_dim() const { return feature_dim_; }
-  const FeaturePipelineConfig& config() const { return config_; }
-
-  // Call when the speech input ends; never call AcceptWaveform() afterwards.
-  void set_input_finished();
-  bool input_finished() const { return input_finished_; }
-
-  // Blocking: false once the input is finished and the queue is empty.
-  bool ReadOne(std::vector<float>* feat);
-  // Blocking: false if fewer than num_frames could be read before the end of input.
-  bool Read(int num_frames, std::vector<std::vector<float>>* feats);
-
-  void Reset();
-  bool IsLastFrame(int frame) const { return input_finished_ && (frame == num_frames_ - 1); }
   int NumQueuedFrames() const;
+  bool input_finished() const { return input_finished_; }
+  bool IsLastFrame(int frame) const { return input_finished_ && (frame == num_frames_ - 1); }
+  const FeaturePipelineConfig& config() const { return config_; }
 
  private:
   const FeaturePipelineConfig config_;
   int feature_dim_;
+  // device side: front-end handle, stream, staging buffers (grown on demand)
   wekws_fbank* fbank_ = nullptr;
   void* stream_ = nullptr;
   float* d_wav_ = nullptr;
   float* d_feat_ = nullptr;
-  float* h_feat_ = nullptr;      // pinned
+  float* h_feat_ = nullptr;                        // pinned
   size_t wav_capacity_ = 0, feat_capacity_ = 0;
-
+  // host side: produced rows, carry-over samples, end-of-input flag
   std::deque<std::vector<float>> feature_queue_;
+  std::vector<float> remained_wav_;
   int num_frames_ = 0;
   bool input_finished_ = false;
-  std::vector<float> remained_wav_;   // samples after the last complete frame shift, kept for the next call
   mutable std::mutex mutex_;
   std::condition_variable finish_condition_;
 };
