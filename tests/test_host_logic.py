@@ -120,6 +120,74 @@ def test_fold_and_pack_reproduce_the_oracle(case, native):
     assert (c - c_ref).abs().max() <= 2e-5 * max(1.0, float(c_ref.abs().max()))
 
 
+@pytest.mark.parametrize("name", ["mdtc", "tcn", "ds_tcn"])
+def test_tensor_core_weight_images_encode_the_folded_gemms(name, native):
+    """The pre-swizzled bf16 hi|lo images the tcgen05 kernels read (K-major SWIZZLE_128B, tc_common.cuh) decode back
+    to the folded FP32 GEMM matrices of the FP32 path: hi = bf16_rn(w), |hi + lo - w| <= 2^-16 |w|, zero padding
+    beyond K.  Pins write_w_image / write_w_image128 and the image order without a GPU."""
+    import ctypes as C
+    import numpy as np
+    cfg = model_config(name)
+    model = synth.randomize_(init_model(cfg)).eval()
+    h = model._build_handle(finalize=False)
+    stream, _ = PE.read_packed(native, h)
+    lib = native.lib()
+    n = lib.wekws_model_packed_floats(h, 2)
+    assert n > 0, "no tensor-core images packed"
+    raw = torch.empty(n, dtype=torch.float32)
+    native.check(lib.wekws_model_packed_copy(h, 2, C.c_void_p(raw.data_ptr()), n), "packed_copy")
+    img = raw.numpy().view(np.uint16)
+    Cc, idim = model.hdim, cfg["input_dim"]
+    K = cfg["backbone"].get("kernel_size", 8)
+    nblk = 17 if name == "mdtc" else 4
+    # FP32 stream: W^T [K][C] matrices in consumption order
+    mats, pos = [], 0
+
+    def take(rows):
+        nonlocal pos
+        w = stream[pos:pos + rows * Cc].reshape(rows, Cc).numpy()
+        pos += rows * Cc
+        return w
+    mats.append(take(idim))
+    per_block = {"mdtc": 2, "tcn": K, "ds_tcn": 1}[name]
+    for _ in range(nblk * per_block):
+        mats.append(take(Cc))
+    assert pos == stream.numel()
+
+    def decode(off_u16, rows):                       # -> (hi, lo) float arrays [rows][64] of one image
+        nn, kk = np.meshgrid(np.arange(rows), np.arange(64), indexing="ij")
+        byte = nn * 128 + (((kk >> 3) ^ (nn & 7)) << 4) + (kk & 7) * 2
+        def f(u):
+            return (u.astype(np.uint32) << 16).view(np.float32)
+        return f(img[off_u16 + byte // 2]), f(img[off_u16 + rows * 64 + byte // 2])
+
+    def check(hi, lo, w):                            # w [rows_n][64 k] (zero where k >= K of the matrix)
+        rn = torch.from_numpy(w.copy()).to(torch.bfloat16).float().numpy()
+        assert np.array_equal(hi, rn)
+        assert np.all(np.abs(hi + lo - w) <= 2.0 ** -16 * np.abs(w) + 1e-30)
+
+    def slab(m, k0, n0, rows):                       # W^T [K][C] -> [n][k] block, zero padded in k
+        out = np.zeros((rows, 64), np.float32)
+        kend = min(k0 + 64, m.shape[0])
+        if kend > k0:
+            out[:, :kend - k0] = m[k0:kend, n0:n0 + rows].T
+        return out
+
+    u = 0
+    if name == "ds_tcn":
+        plan = [(0, 64 * a, 128 * hh) for a in range((idim + 63) // 64) for hh in range(2)]
+        plan += [(1 + b, 64 * ks, 128 * hh) for b in range(nblk) for ks in range(4) for hh in range(2)]
+        rows = 128
+    else:
+        plan = [(0, 0, 0), (0, 64, 0)] + [(1 + g, 0, 0) for g in range(nblk * per_block)]
+        rows = 64
+    for mi, k0, n0 in plan:
+        hi, lo = decode(u, rows)
+        check(hi, lo, slab(mats[mi], k0, n0, rows))
+        u += rows * 64 * 2
+    assert u == img.size
+
+
 def test_state_dict_schema_and_init_match_reference_golden():
     d = golden("init_digest")
     for name in ("mdtc", "mdtc_small", "ds_tcn", "tcn", "gru"):

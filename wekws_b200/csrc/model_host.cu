@@ -538,11 +538,17 @@ extern "C" int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T) {
 
 extern "C" int64_t wekws_model_packed_floats(const wekws_model* m, int which) {
   if (!m) return 0;
+  if (which == 2) return (int64_t)(m->h_wimg.size() / sizeof(float));     // tensor-core weight images, raw bytes
   return which == 0 ? (int64_t)m->h_stream.size() : (int64_t)m->h_vec.size();
 }
 
 extern "C" int wekws_model_packed_copy(const wekws_model* m, int which, float* h_dst, int64_t capacity) {
   WEKWS_REQUIRE(m && h_dst, "wekws_model_packed_copy: null argument");
+  if (which == 2) {
+    WEKWS_REQUIRE((int64_t)(m->h_wimg.size() / sizeof(float)) <= capacity, "wekws_model_packed_copy: capacity too small");
+    memcpy(h_dst, m->h_wimg.data(), m->h_wimg.size());
+    return WEKWS_OK;
+  }
   const std::vector<float>& v = which == 0 ? m->h_stream : m->h_vec;
   WEKWS_REQUIRE((int64_t)v.size() <= capacity, "wekws_model_packed_copy: capacity too small");
   memcpy(h_dst, v.data(), v.size() * sizeof(float));
