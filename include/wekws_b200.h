@@ -160,7 +160,9 @@ WEKWS_API int wekws_model_packed_copy(const wekws_model* m, int which, float* h_
 
 /* d_feats (B,T,idim); d_in_cache NULL (start of stream == zeros) or
  * conv: (B,hdim,padding)  GRU: (num_layers,B,hdim); d_out (B,T,odim);
- * d_out_cache same shape as the cache (may alias d_in_cache).                       */
+ * d_out_cache same shape as the cache; it may be the SAME buffer as d_in_cache (in-place
+ * streaming update: every slice is read before it is overwritten) or a disjoint one, not a
+ * partially overlapping one.                                                       */
 WEKWS_API int wekws_model_forward(wekws_model* m, const float* d_feats, const float* d_in_cache,
                         float* d_out, float* d_out_cache, int64_t B, int64_t T,
                         uint32_t flags, void* stream);
