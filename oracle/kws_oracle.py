@@ -276,6 +276,46 @@ def _gru(x, cache, sd, bb, hdim):
         return g(x, cache)
 
 
+def _fsmn(x, cache, sd, bb):
+    """FSMN backbone (wekws/model/fsmn.py:401-495; SURVEY 8f-4 -- oracle only, no product kernel yet).
+    in_linear1 -> in_linear2 -> ReLU -> num_layers x [LinearTransform (no bias) -> FSMNBlock -> AffineTransform ->
+    ReLU] -> out_linear1 -> out_linear2.  FSMNBlock (fsmn.py:173-253): with p = cat(cache, h) along time
+    (cache = (lorder-1) lstride + rorder rstride columns, zeros at the start of a stream),
+        out[t] = p[t + (lorder-1) lstride] + sum_i wl[i] p[t + i lstride] + sum_j wr[j] p[t + (lorder-1) lstride + (j+1) rstride]
+    i.e. the output is delayed by rorder*rstride frames; new cache = last columns of p.  The 4-D cache is
+    (B, proj_dim, cache_len, num_layers)."""
+    L, lo, ro = bb["num_layers"], bb["left_order"], bb["right_order"]
+    # the reference builds every block with strides (1, 1) whatever the config says (_build_repeats, fsmn.py:384-391
+    # passes the literals 1, 1); left_stride / right_stride only enter FSMN.padding, which the forward never uses
+    ls, rs = 1, 1
+    assert ro >= 1, "the reference's FSMNBlock slices x_pad[:, :, :-rorder*rstride] and breaks for right_order = 0"
+    pad = (lo - 1) * ls + ro * rs
+    B, T, _ = x.shape
+    h = F.linear(x, sd["backbone.in_linear1.linear.weight"], sd["backbone.in_linear1.linear.bias"])
+    h = F.relu(F.linear(h, sd["backbone.in_linear2.linear.weight"], sd["backbone.in_linear2.linear.bias"]))
+    new_caches = []
+    for l in range(L):
+        pre = f"backbone.fsmn.{l}."
+        p = F.linear(h, sd[pre + "0.linear.weight"])                               # (B, T, proj)
+        pt = p.transpose(1, 2)                                                      # (B, proj, T)
+        c = pt.new_zeros(B, pt.size(1), pad) if cache is None else cache[:, :, :, l]
+        cat = torch.cat((c, pt), dim=2)                                             # fsmn.py:226-231
+        new_caches.append(cat[:, :, -pad:] if pad > 0 else cat[:, :, :0])           # :232-233
+        wl = sd[pre + "1.conv_left.weight"].reshape(-1, lo)                          # (proj, lorder)
+        out = cat[:, :, (lo - 1) * ls:(lo - 1) * ls + T].clone()                     # :238-239
+        for i in range(lo):
+            out = out + wl[:, i].reshape(1, -1, 1) * cat[:, :, i * ls:i * ls + T]    # :235-237 (valid conv, dilation ls)
+        if ro > 0:
+            wr = sd[pre + "1.conv_right.weight"].reshape(-1, ro)
+            base = (lo - 1) * ls + rs                                                # :241-248
+            for j in range(ro):
+                out = out + wr[:, j].reshape(1, -1, 1) * cat[:, :, base + j * rs:base + j * rs + T]
+        h = F.relu(F.linear(out.transpose(1, 2), sd[pre + "2.linear.weight"], sd[pre + "2.linear.bias"]))
+    h = F.linear(h, sd["backbone.out_linear1.linear.weight"], sd["backbone.out_linear1.linear.bias"])
+    h = F.linear(h, sd["backbone.out_linear2.linear.weight"], sd["backbone.out_linear2.linear.bias"])
+    return h, torch.stack(new_caches, dim=3)
+
+
 def backbone_padding(cfg: dict) -> int:
     bb = cfg["backbone"]
     if bb["type"] == "mdtc":
@@ -298,8 +338,13 @@ def kws_forward(sd: Dict[str, Tensor], cfg: dict, feats: Tensor,
     if "global_cmvn.mean" in sd:
         x = global_cmvn(x, sd["global_cmvn.mean"], sd["global_cmvn.istd"],
                         cfg.get("cmvn", {}).get("norm_var", True))
-    x = F.relu(F.linear(x, sd["preprocessing.out.0.weight"], sd["preprocessing.out.0.bias"]))
     bb = cfg["backbone"]
+    if bb["type"] == "fsmn":      # preprocessing 'none' (NoSubsampling), classifier 'identity' (kws_model.py:121-122,191)
+        x, new_cache = _fsmn(x, cache, sd, bb)
+        if cfg.get("activation", {}).get("type", "sigmoid") != "identity":
+            x = torch.sigmoid(x)
+        return (x.softmax(2) if softmax else x), new_cache
+    x = F.relu(F.linear(x, sd["preprocessing.out.0.weight"], sd["preprocessing.out.0.bias"]))
     if bb["type"] == "mdtc":
         x, new_cache = _mdtc(x, cache, sd, bb)
     elif bb["type"] == "tcn":

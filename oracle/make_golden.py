@@ -103,6 +103,32 @@ def gen_fbank():
     print("fbank cases", len(waves))
 
 
+def gen_fsmn():
+    """FSMN backbone from the live reference: weights, chunked streaming with the 4-D cache, and the
+    whole utterance in one call."""
+    from wekws.model.kws_model import init_model
+    from tests.cases import FSMN_CASES, fsmn_config
+    for case in FSMN_CASES:
+        cfg = fsmn_config(case)
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(777)
+            model = init_model(cfg)
+        model.eval()
+        arrays = {"sd_" + k: v.numpy() for k, v in model.state_dict().items()}
+        cache = torch.zeros(0, 0, 0, 0)
+        xs = []
+        with torch.no_grad():
+            for i, T in enumerate(CHUNKS + (9,)):
+                x = synth.features(2, T, cfg["input_dim"], seed=300 + i)
+                xs.append(x)
+                y, cache = model(x, cache)
+                arrays[f"x{i}"], arrays[f"y{i}"], arrays[f"c{i}"] = x.numpy(), y.numpy(), cache.numpy()
+            yf, _ = model(torch.cat(xs, dim=1), torch.zeros(0, 0, 0, 0))
+            arrays["y_full"] = yf.numpy()
+        np.savez_compressed(os.path.join(OUT, f"model_{case}.npz"), **arrays)
+        print(case, "cache", tuple(cache.shape))
+
+
 def gen_mfcc():
     """kaldi.mfcc exactly as wekws/dataset/processor.py:157-166 calls it (the mdtc configs: num_ceps = num_mel_bins = 80)."""
     import torchaudio.compliance.kaldi as kaldi
@@ -147,6 +173,7 @@ if __name__ == "__main__":
     gen_models()
     gen_fbank()
     gen_mfcc()
+    gen_fsmn()
     gen_cmvn()
     gen_init_parity()
     print("golden vectors written to", OUT)

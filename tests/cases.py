@@ -15,6 +15,21 @@ MODEL_CASES = [
     ("gru", "gru", dict(), 3),
     ("gru_cmvn", "gru", dict(cmvn=True, input_dim=40, output_dim=2), 2),
 ]
+# FSMN: oracle-only cases -- the product has no FSMN kernel yet.  Small dims (the goldens carry the
+# weights), the shipped orders (fsmn_ctc.yaml:42-52) and a strided variant.
+FSMN_CASES = {
+    "fsmn": dict(left_order=10, right_order=2, left_stride=1, right_stride=1),
+    "fsmn_strided": dict(left_order=4, right_order=1, left_stride=2, right_stride=3),   # strides are ignored upstream
+}
+
+
+def fsmn_config(case: str) -> dict:
+    bb = dict(type="fsmn", input_affine_dim=24, num_layers=3, linear_dim=36, proj_dim=16, output_affine_dim=20)
+    bb.update(FSMN_CASES[case])
+    return dict(input_dim=40, output_dim=7, hidden_dim=16, preprocessing=dict(type="none"), backbone=bb,
+                classifier=dict(type="identity", dropout=0.1), activation=dict(type="identity"))
+
+
 CHUNKS = (40, 17, 1)   # streamed back to back, cache carried (17 < pad of the dilation-8 blocks)
 CASE_NAMES = [c[0] for c in MODEL_CASES]
 

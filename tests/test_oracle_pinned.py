@@ -60,6 +60,26 @@ def test_oracle_fbank_matches_reference_golden():
     assert np.all(z == np.float32(np.log(np.float32(O.EPS))))
 
 
+@pytest.mark.parametrize("case", ["fsmn", "fsmn_strided"])
+def test_oracle_fsmn_matches_reference_golden(case):
+    """SURVEY 8f-4 groundwork: the FSMN restatement against the real reference (weights travel in the golden file)."""
+    from tests.cases import fsmn_config
+    g = golden("model_" + case)
+    cfg = fsmn_config(case)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}
+    cache, i = None, 0
+    while f"x{i}" in g.files:
+        y, cache = O.kws_forward(sd, cfg, torch.from_numpy(g[f"x{i}"]), cache)
+        assert np.abs(y.numpy() - g[f"y{i}"]).max() <= TOL_MODEL * max(1.0, np.abs(g[f"y{i}"]).max()), (case, i)
+        assert cache.shape == g[f"c{i}"].shape and np.abs(cache.numpy() - g[f"c{i}"]).max() <= 1e-5
+        i += 1
+    assert i == 4
+    # streaming == whole utterance (the right context only delays the output, fsmn.py:238-248)
+    full = torch.cat([torch.from_numpy(g[f"x{j}"]) for j in range(i)], dim=1)
+    yf, _ = O.kws_forward(sd, cfg, full, None)
+    assert np.abs(yf.numpy() - g["y_full"]).max() <= TOL_MODEL * max(1.0, np.abs(g["y_full"]).max())
+
+
 def test_oracle_mfcc_matches_reference_golden():
     """kaldi.mfcc as wekws/dataset/processor.py:157-166 calls it (fixtures from oracle/make_golden.py gen_mfcc)."""
     g, fb = golden("mfcc"), golden("fbank")
