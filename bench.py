@@ -394,6 +394,20 @@ def main():
                      "note": "HBM fraction as SURVEY 8d asks; the fused backbone is instruction/shared-memory bound "
                              "(DESIGN.md section 4)"},
     }
+    # SURVEY 8d second figure for the tensor-core kernels: bf16 tensor-pipe utilisation = dense GEMM FLOP/frame x 3
+    # passes of the bf16x3 split / measured bf16 peak (MEASURED_PEAKS.json); informational, never fatal
+    try:
+        dense = {"mdtc": 34 * 2 * 64 * 64 + 2 * 80 * 64, "tcn": 32 * 2 * 64 * 64 + 2 * 80 * 64,
+                 "ds_tcn": 4 * 2 * 256 * 256 + 2 * 80 * 256}.get(model_name)
+        if dense and line["tensor_cores"] and not pcm_mode:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                pk = json.load(f)
+            bf16_peak = float(pk.get("bf16_tflops", pk.get("bf16_tflops_burst", 0)) or 0)
+            tf = 3.0 * dense * B * T / (launch_ms * 1e-3) / 1e12
+            line["roofline"]["tensor_pipe"] = {"achieved_bf16_tflops": tf, "peak_bf16_tflops": bf16_peak or None,
+                                               "frac": (tf / bf16_peak) if bf16_peak else None, "passes": 3}
+    except Exception:
+        pass
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(model_name, B, T, idim, steps=40, warmup=2, budget_s=15.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
