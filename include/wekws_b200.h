@@ -169,13 +169,14 @@ WEKWS_API int wekws_model_forward(wekws_model* m, const float* d_feats, const fl
 
 /* Detection statistics of max-pooling keyword models on the device, bit-exact with the host
  * pipeline wekws/bin/score.py:128-137 ('{:.6f}' score file) -> wekws/bin/compute_det.py:76-105:
- *   d_max_score[b,k]   = max over the first lens[b] frames of the text-rounded posterior (false-reject test),
+ *   d_max_score[b,k]   = max over the first lens[b] frames of the text-rounded posterior as the DOUBLE Python parses
+ *                        back from the score file (false-reject test `max < threshold` is done in double),
  *   d_triggers[b,k,i]  = triggers of the left-to-right scan "score >= thresholds[i] -> count, skip window_shift
  *                        frames" (false alarms).
  * d_post (B,T,K) posteriors; d_lens NULL = all T frames; d_thresholds nthr doubles (the host accumulates
  * threshold += step exactly as the reference does).                                                   */
 WEKWS_API int wekws_det_stats(const float* d_post, const int32_t* d_lens, int64_t B, int64_t T, int K,
-                    const double* d_thresholds, int nthr, int window_shift, float* d_max_score,
+                    const double* d_thresholds, int nthr, int window_shift, double* d_max_score,
                     int32_t* d_triggers, void* stream);
 
 /* Raw PCM -> posteriors: Fbank(+CMVN from the model's global_cmvn.* if set) -> model.

@@ -391,3 +391,28 @@ def det_stats(post: Tensor, lengths, step: float = 0.01, window_shift: int = 50)
                 row.append(count)
             triggers[b][k] = row
     return thresholds, max_score, triggers
+
+
+def det_curve_text(thresholds, max_score, triggers, kinds, durations, k: int) -> str:
+    """The stats file wekws/bin/compute_det.py:76-105 writes for keyword index k, from det_stats outputs:
+    kinds[b] == k marks keyword utterances (compute_det.py:44-46), every other utterance is filler and adds its
+    duration (:47-49).  Pinned by tests/golden/det_stats.npz, which the reference tool itself wrote
+    (oracle/make_det_golden.py)."""
+    B = len(kinds)
+    kw = [b for b in range(B) if kinds[b] == k]
+    fil = [b for b in range(B) if kinds[b] != k]
+    filler_duration = 0.0
+    for b in fil:
+        filler_duration += float(durations[b])
+    lines = []
+    false_reject_rate = false_alarm_per_hour = None
+    for i, threshold in enumerate(thresholds):
+        num_false_reject = sum(1 for b in kw if float(max_score[b][k]) < threshold)          # :81-85
+        num_false_alarm = sum(triggers[b][k][i] for b in fil)                                # :86-97
+        if len(kw) != 0:
+            false_reject_rate = num_false_reject / len(kw)
+        num_false_alarm = max(num_false_alarm, 1e-6)
+        if filler_duration != 0:
+            false_alarm_per_hour = num_false_alarm / (filler_duration / 3600.0)
+        lines.append('{:.6f} {:.6f} {:.6f}\n'.format(threshold, false_alarm_per_hour, false_reject_rate))
+    return ''.join(lines)

@@ -310,6 +310,18 @@ def test_native_runtime_shim_streams_like_the_python_model(case, batch, models, 
     ref = torch.cat(ref)
     assert got.shape == ref.shape
     assert (got - ref).abs().max() <= 2e-6          # same kernels, same chunking: only the 9-digit text round trip
+    # ... and against the CPU oracle streamed with the same chunking and resets (the checker proper)
+    oref, ocache, nb = [], None, 0
+    for s0 in range(0, T, batch):
+        if ocache is None and gru:
+            ocache = torch.zeros(cfg["backbone"]["num_layers"], 1, cfg["hidden_dim"])
+        y, ocache = O.kws_forward(sd, cfg, x[:, s0:s0 + batch], ocache)
+        oref.append(y[0])
+        nb += 1
+        if nb % reset_every == 0:
+            ocache = None
+    oref = torch.cat(oref)
+    assert (got - oref).abs().max() <= _tol(oref.numpy())
 
 
 def test_native_runtime_pcm_to_posterior_like_kws_main(models, tmp_path):
@@ -339,6 +351,14 @@ def test_native_runtime_pcm_to_posterior_like_kws_main(models, tmp_path):
     # the C++ window / mel tables are built in double, the Python ones with torch fp32 ops: the features differ in
     # the last bits and the posteriors by 2.4e-5 (measured) -- the posterior gate applies
     assert (got - ref).abs().max() <= TOL_POST
+    # ... and against the CPU oracle: Hamming-window Fbank (pinned to the compiled reference front-end by
+    # tests/test_compiled_reference.py) -> reference forward with the same 32-frame batches
+    ofeats = O.fbank(pcm.float(), window_type="hamming").unsqueeze(0)
+    oref, ocache = [], None
+    for s0 in range(0, T, batch):
+        y, ocache = O.kws_forward(sd, cfg, ofeats[:, s0:s0 + batch], ocache)
+        oref.append(y[0])
+    assert (got - torch.cat(oref)).abs().max() <= TOL_POST
 
 
 def test_det_stats_bit_exact_with_score_file_pipeline():
@@ -356,17 +376,36 @@ def test_det_stats_bit_exact_with_score_file_pipeline():
         o_thr, o_ms, o_tr = O.det_stats(post, lens, 0.01, ws)
         assert thr.tolist() == o_thr and len(o_thr) in (100, 101)
         assert tr.cpu().tolist() == o_tr, ws
-        got = ms.cpu().double()
+        got = ms.cpu()
+        assert got.dtype == torch.float64          # compared in double like compute_det.py:84
         for b in range(B):
             for k in range(K):
-                want = o_ms[b][k]
-                assert (got[b, k].item() == float(torch.tensor(want, dtype=torch.float32))) or (want == float("-inf") and got[b, k].item() == want)
+                assert got[b, k].item() == o_ms[b][k], (b, k)
     thr, ms, tr = det_stats(post.to(DEV), None, window_shift=50)
     assert tr.cpu().tolist() == O.det_stats(post, None, 0.01, 50)[2]
     rows = det_curve(thr, ms, tr, [True, False, True, False, False, False, True], filler_hours=0.5)
     assert len(rows) == thr.numel() and rows[0][2] == 0.0 and rows[-1][1] >= 0.0
     with pytest.raises(RuntimeError):
         det_stats(post)
+
+
+def test_det_stats_reproduces_reference_compute_det_files():
+    """Device sweep + det_curve == the stats files written by the reference's own compute_det.py (golden made by
+    oracle/make_det_golden.py): thresholds, false alarms per hour and false-reject rates, text for text."""
+    from wekws_b200 import det_curve, det_stats
+    g = golden("det_stats")
+    post, lens = torch.from_numpy(g["post"]).to(DEV), torch.from_numpy(g["lens"]).to(DEV)
+    kinds, durs = g["kinds"].tolist(), g["durations"].tolist()
+    for si, (ws, step) in enumerate(g["settings"].tolist()):
+        thr, ms, tr = det_stats(post, lens, step=step, window_shift=int(ws))
+        for k in range(post.shape[2]):
+            filler = 0.0
+            for b, kd in enumerate(kinds):
+                if kd != k:
+                    filler += durs[b]
+            rows = det_curve(thr, ms, tr, [kd == k for kd in kinds], filler_hours=filler / 3600.0, keyword_index=k)
+            text = "".join("{:.6f} {:.6f} {:.6f}\n".format(*r) for r in rows)
+            assert text == str(g[f"stats_{si}_{k}"]), (si, k)
 
 
 def test_launch_counter_counts_our_kernels(native, models):

@@ -1,0 +1,187 @@
+"""Round-2 parity cases (VERDICT r01 "What's weak" 1-4): BASELINE.json shapes that had no test, absolute
+1e-4 gates on SIGMOID posteriors over >= 1000 clips, the hidden-32 tile bug, stale weight packs, patch_reference().
+Everything goes through the C ABI; the checker is oracle/kws_oracle.py (pinned to the reference's goldens)."""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kws_oracle as O
+from tests.cases import build_model
+from wekws_b200 import Fbank, Mfcc, init_model, model_config, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_POST = 1e-4          # north_star: <= 1e-4 max-abs on the posterior scores, ABSOLUTE (no magnitude scaling here)
+
+
+def _model(name, seed=777, **kw):
+    cmvn = kw.pop("cmvn", False)
+    cmvn_file = synth.write_cmvn_json(kw.get("input_dim", 80)) if cmvn else None
+    try:
+        cfg = model_config(name, cmvn_file=cmvn_file, **kw)
+        torch.manual_seed(seed)
+        m = synth.randomize_(init_model(cfg), seed=seed).eval()
+    finally:
+        if cmvn_file:
+            os.unlink(cmvn_file)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    return cfg, m.to(DEV), sd
+
+
+@pytest.mark.parametrize("cmvn", [True, False])
+def test_pcm_to_sigmoid_posterior_1250_clips(cmvn):
+    """BASELINE configs[4] per-GPU shape: 1250 one-second clips, raw int16 PCM -> Fbank (-> CMVN) -> mdtc -> sigmoid.
+    Max-abs error over all 1250 x 98 posteriors against the CPU oracle (torchaudio-equivalent Fbank + reference
+    forward) <= 1e-4 absolute."""
+    cfg, m, sd = _model("mdtc", cmvn=cmvn)
+    pcm = synth.pcm_int16(1250, 16000, seed=1234)
+    y, c = m(Fbank(80)(pcm.to(DEV)))
+    ref_f = torch.stack([O.fbank(pcm[b].float()) for b in range(pcm.shape[0])])
+    y_ref, c_ref = O.kws_forward(sd, cfg, ref_f, None)
+    err = float((y.cpu() - y_ref).abs().max())
+    cerr = float(((c.cpu() - c_ref).abs() / c_ref.abs().clamp_min(1.0)).max())
+    print(f"pcm->posterior 1250 clips cmvn={cmvn}: posterior max-abs {err:.3e}, cache rel {cerr:.3e}, "
+          f"posterior range [{float(y_ref.min()):.3f}, {float(y_ref.max()):.3f}]")
+    assert y.shape == (1250, 98, 1) and err <= TOL_POST
+    assert cerr <= 2e-3
+
+
+def test_mfcc_to_sigmoid_posterior_1000_clips():
+    """The shipped mdtc front-end (mdtc.yaml:8-14: mfcc, 80 ceps) -> mdtc -> sigmoid over 1000 clips, absolute gate."""
+    cfg, m, sd = _model("mdtc", cmvn=True)
+    pcm = synth.pcm_int16(1000, 16000, seed=99)
+    y, _ = m(Mfcc(80, 80)(pcm.to(DEV)))
+    ref_f = torch.stack([O.mfcc(pcm[b].float(), 80, 80) for b in range(pcm.shape[0])])
+    y_ref, _ = O.kws_forward(sd, cfg, ref_f, None)
+    err = float((y.cpu() - y_ref).abs().max())
+    print(f"mfcc->posterior 1000 clips: posterior max-abs {err:.3e}")
+    assert err <= TOL_POST
+
+
+def test_gru_b512_t1_fifty_carried_steps():
+    """BASELINE configs[2]: GRU hidden 128, 512 streams, one frame per call, h carried over 50 calls."""
+    cfg, m, sd = _model("gru")
+    B, steps = 512, 50
+    x = synth.features(B, steps, 80, seed=21)
+    h = torch.zeros(2, B, 128)
+    hd = h.to(DEV)
+    worst = 0.0
+    for t in range(steps):
+        y, hd = m(x[:, t:t + 1].to(DEV), hd)
+        y_ref, h = O.kws_forward(sd, cfg, x[:, t:t + 1], h)
+        worst = max(worst, float((y.cpu() - y_ref).abs().max()))
+        assert worst <= TOL_POST, (t, worst)
+    assert float((hd.cpu() - h).abs().max()) <= TOL_POST
+    print(f"gru B=512 T=1 x 50 steps: posterior max-abs {worst:.3e}")
+
+
+@pytest.mark.parametrize("B,T", [(4, 40), (3, 13), (64, 40)])
+def test_ds_tcn_ctc_vocabulary_2599(B, T):
+    """The shipped CTC configuration (ds_tcn_ctc.yaml:31-42: hidden 256, output_dim 2599, identity activation):
+    logits, softmax posteriors (forward_softmax, export_onnx.py:46-48) and the cache."""
+    cfg, m, sd = _model("ds_tcn", activation="identity", output_dim=2599, input_dim=40)
+    x = synth.features(B, T, 40, seed=8)
+    cache = torch.randn(B, 256, 105, generator=torch.Generator().manual_seed(4))
+    y, c = m(x.to(DEV), cache.to(DEV))
+    p, _ = m.forward_softmax(x.to(DEV), cache.to(DEV))
+    y_ref, c_ref = O.kws_forward(sd, cfg, x, cache)
+    p_ref, _ = O.kws_forward(sd, cfg, x, cache, softmax=True)
+    scale = max(1.0, float(y_ref.abs().max()))
+    err, perr = float((y.cpu() - y_ref).abs().max()), float((p.cpu() - p_ref).abs().max())
+    print(f"ds_tcn_ctc odim 2599 B={B} T={T}: logits max-abs {err:.3e} (|y|max {scale:.2f}), softmax max-abs {perr:.3e}")
+    assert y.shape == (B, T, 2599)
+    assert err <= TOL_POST * scale and perr <= TOL_POST
+    assert float((c.cpu() - c_ref).abs().max()) <= TOL_POST * max(1.0, float(c_ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,T", [(1024, 40), (1, 300), (300, 1), (9, 57)])
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
+def test_mdtc_small_large_tiles(B, T, precision):
+    """hidden 32 tiles with more than 256 rows (B=1024 x T=40 packs 7 streams = 280 rows; one
+    utterance of 300 frames) ran the time-parallel loops over the first 256 rows only."""
+    cfg, m, sd = _model("mdtc_small", input_dim=40)
+    m.precision = precision
+    x = synth.features(B, T, 40, seed=31)
+    cache = torch.randn(B, 32, 184, generator=torch.Generator().manual_seed(6))
+    y, c = m(x.to(DEV), cache.to(DEV))
+    y_ref, c_ref = O.kws_forward(sd, cfg, x, cache)
+    err = float((y.cpu() - y_ref).abs().max())
+    cerr = float((c.cpu() - c_ref).abs().max())
+    assert err <= TOL_POST, (B, T, err)
+    assert cerr <= TOL_POST * max(1.0, float(c_ref.abs().max())), (B, T, cerr)
+
+
+def test_in_place_weight_edits_repack():
+    """optimizer-style in-place edits and sub-module load_state_dict must not run stale packs."""
+    cfg, m, sd = _model("tcn")
+    x = synth.features(3, 24, 80, seed=2)
+    y0, _ = m(x.to(DEV))
+    with torch.no_grad():
+        m.classifier.linear.bias.add_(0.75)
+    sd2 = {k: v.clone().cpu() for k, v in m.state_dict().items()}
+    y1, _ = m(x.to(DEV))
+    assert float((y1 - y0).abs().max()) > 1e-3
+    assert float((y1.cpu() - O.kws_forward(sd2, cfg, x, None)[0]).abs().max()) <= TOL_POST
+    m.backbone.load_state_dict({k: torch.zeros_like(v) if k.endswith("cnn.0.weight") else v
+                                for k, v in m.backbone.state_dict().items()})
+    sd3 = {k: v.clone().cpu() for k, v in m.state_dict().items()}
+    y2, _ = m(x.to(DEV))
+    assert float((y2.cpu() - O.kws_forward(sd3, cfg, x, None)[0]).abs().max()) <= TOL_POST
+
+
+def test_patch_reference_score_loop(tmp_path):
+    """wekws/bin/score.py:109-137 restated around `wekws.model.kws_model` after patch_reference(): the reference's
+    own import line resolves to this implementation, a reference-format checkpoint loads strictly, a zero-padded
+    ragged batch is scored, and the '{:.6f}' score lines equal the oracle's to the text precision."""
+    from wekws_b200 import patch_reference
+    cfg, m0, sd = _model("mdtc", cmvn=True, output_dim=2)
+    ckpt = tmp_path / "avg_3.pt"
+    torch.save(sd, str(ckpt))
+    patched_real = patch_reference()
+    assert patched_real is False or os.path.isdir("/root/reference")
+    from wekws.model.kws_model import init_model as ref_named_init        # score.py:30
+    import wekws_b200.kws_model as ours
+    assert ref_named_init is ours.init_model
+    cmvn_file = synth.write_cmvn_json(80)
+    try:
+        configs = {"model": model_config("mdtc", cmvn_file=cmvn_file, output_dim=2)}
+        model = ref_named_init(configs["model"])                          # score.py:108
+    finally:
+        os.unlink(cmvn_file)
+    checkpoint = torch.load(str(ckpt), map_location="cpu")                # utils/checkpoint.py:23-30
+    model.load_state_dict(checkpoint, strict=True)
+    device = torch.device("cuda")                                         # score.py:110-113
+    model = model.to(device)
+    model.eval()
+    lens = torch.tensor([98, 61, 98, 7, 33])
+    pcm = synth.pcm_int16(5, 16000, seed=77)
+    feats_cpu = torch.stack([O.fbank(pcm[b].float()) for b in range(5)])
+    for b in range(5):
+        feats_cpu[b, lens[b]:] = 0.0                                      # pad_sequence zero padding (processor.py)
+    keys = ["utt%d" % i for i in range(5)]
+    fout = io.StringIO()
+    with torch.no_grad():                                                 # score.py:116-137
+        feats = feats_cpu.to(device)
+        feats_lengths = lens.to(device)
+        logits, _ = model(feats)
+        num_keywords = logits.shape[2]
+        logits = logits.cpu()
+        for i in range(len(keys)):
+            score = logits[i][:feats_lengths[i]]
+            for keyword_i in range(num_keywords):
+                keyword_scores = score[:, keyword_i]
+                score_frames = " ".join(["{:.6f}".format(x) for x in keyword_scores.tolist()])
+                fout.write("{} {} {}\n".format(keys[i], "kw%d" % keyword_i, score_frames))
+    y_ref, _ = O.kws_forward(sd, cfg, feats_cpu, None)
+    lines = fout.getvalue().splitlines()
+    assert len(lines) == 10
+    for ln in lines:
+        arr = ln.split()
+        i, k = int(arr[0][3:]), int(arr[1][2:])
+        got = np.array(list(map(float, arr[2:])))
+        want = y_ref[i, :lens[i], k].numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= TOL_POST + 1e-6

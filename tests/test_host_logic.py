@@ -258,3 +258,31 @@ def test_cmvn_loaders(tmp_path):
                  "<Rescale> 2 2\n<LearnRateCoef> 0 [ 0.5 0.25 ]\n</Nnet>\n")
     out = load_kaldi_cmvn(str(k))
     assert out.shape == (2, 6) and np.allclose(out[0, :2], [1.5, 2.5]) and np.allclose(out[1, :2], [0.5, 0.25])
+
+
+def test_patch_reference_rebinds_the_reference_factory():
+    """patch_reference() (wekws_b200/overlay.py): with the reference importable, `wekws.model.kws_model.init_model`
+    and `.KWSModel` -- the names wekws/bin/score.py:30 and average_model / stream_kws_ctc import -- become this
+    implementation; without it a stub package of the same dotted name is registered.  Run in subprocesses so the
+    live-reference tests of this session keep the unpatched module."""
+    import subprocess
+    import sys
+    from tests.conftest import ROOT, have_reference
+    code_stub = ("import sys; sys.path.insert(0, %r)\n"
+                 "from wekws_b200 import patch_reference; import wekws_b200.kws_model as ours\n"
+                 "assert patch_reference() is False\n"
+                 "from wekws.model.kws_model import init_model, KWSModel\n"
+                 "assert init_model is ours.init_model and KWSModel is ours.KWSModel\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code_stub], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    if not have_reference():
+        return
+    code_real = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, '/root/reference')\n"
+                 "import wekws.model.kws_model as ref; orig = ref.init_model\n"
+                 "from wekws_b200 import patch_reference; import wekws_b200.kws_model as ours\n"
+                 "assert patch_reference() is True\n"
+                 "from wekws.model.kws_model import init_model, KWSModel\n"
+                 "assert init_model is ours.init_model and init_model is not orig and KWSModel is ours.KWSModel\n"
+                 "import wekws.model.mdtc  # the rest of the reference package stays importable\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code_real], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr

@@ -139,3 +139,15 @@ def test_oracle_fbank_matches_live_torchaudio():
     ref = kaldi.fbank(pcm.unsqueeze(0), num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0,
                       energy_floor=0.0, sample_frequency=16000)
     assert (O.fbank(pcm) - ref).abs().max() <= TOL_FBANK
+
+
+def test_oracle_det_stats_pinned_to_reference_compute_det():
+    """O.det_stats + O.det_curve_text == the stats files the REFERENCE's wekws/bin/compute_det.py wrote for the same
+    score / label files (tests/golden/det_stats.npz, made by oracle/make_det_golden.py), byte for byte."""
+    g = golden("det_stats")
+    post, lens = torch.from_numpy(g["post"]), torch.from_numpy(g["lens"])
+    kinds, durs = g["kinds"].tolist(), g["durations"].tolist()
+    for si, (ws, step) in enumerate(g["settings"].tolist()):
+        thr, ms, tr = O.det_stats(post, lens, step, int(ws))
+        for k in range(post.shape[2]):
+            assert O.det_curve_text(thr, ms, tr, kinds, durs, k) == str(g[f"stats_{si}_{k}"]), (si, k)

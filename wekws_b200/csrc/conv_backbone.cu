@@ -80,7 +80,6 @@ struct TileMap {
       valid[t] = r0[t] < RP;
     }
   }
-  static constexpr int max_rows() { return 16 * (16 / (C / 32)) * TPT; }
 };
 
 #define FMA16(ACC, W4, A4)                                                             \
@@ -423,7 +422,12 @@ int conv_chunk_rows(int C) { return C <= 128 ? 64 : 32; }
 namespace {
 constexpr size_t kSmemCap = 227 * 1024;
 
-int max_rows_map(int C) { return 16 * (16 / (C / 32)) * TPT; }
+// rows a tile may hold: what the GEMM tile map covers, capped at the 8 x 32 rows the time-parallel loops
+// (row_s / row_t, depthwise conv, tap copies) walk -- hidden 32 would otherwise map 512 rows
+int max_rows_map(int C) {
+  const int m = 16 * (16 / (C / 32)) * TPT;
+  return m < 256 ? m : 256;
+}
 
 // Shared-memory bytes of a tile of S streams / RP padded rows; *ah = floats of region AH.
 size_t tile_smem(const ConvArgs& a, int S, int RP, int PADMAX, int KP, size_t* ah) {

@@ -453,7 +453,12 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.odim = fb->nceps > 0 ? fb->nceps : fb->cfg.num_mel_bins;
   const long long items = B * ((max_frames + FB_FRAMES - 1) / FB_FRAMES);
   const size_t smem = (size_t)(STAGE + FB_WARPS * 2 * (A_SZ + B_SZ) + 2 * NBIN + WIN + 2 * NBIN + 64) * sizeof(float);
-  static int occ[4] = {0, 0, 0, 0};
+  int dev = 0;
+  WEKWS_CUDA_OK(cudaGetDevice(&dev));
+  WEKWS_REQUIRE(dev == fb->device, "fbank handle was created on device %d but the current device is %d", fb->device, dev);
+  WEKWS_REQUIRE(dev >= 0 && dev < 64, "fbank: device index %d out of range", dev);
+  static int occ_dev[64][4] = {};        // the shared-memory attribute and the occupancy are per device
+  int* occ = occ_dev[dev];
   const bool mf = fb->nceps > 0;
   const int ti = (pcm_dtype == WEKWS_PCM_S16 ? 0 : 1) + (mf ? 2 : 0);
   const void* kern = ti == 0 ? (const void*)fbank_kernel<int16_t, false> : ti == 1 ? (const void*)fbank_kernel<float, false>

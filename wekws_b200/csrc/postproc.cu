@@ -20,7 +20,7 @@ __device__ __forceinline__ double text_round6(float x) { return rint((double)x *
 // posteriors it scans are broadcast loads
 __global__ void det_stats_kernel(const float* __restrict__ post, const int32_t* __restrict__ lens, long long B,
                                  long long T, int K, const double* __restrict__ thr, int nthr, int window_shift,
-                                 float* __restrict__ max_score, int32_t* __restrict__ triggers) {
+                                 double* __restrict__ max_score, int32_t* __restrict__ triggers) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = B * K * (long long)nthr;
   if (idx >= total) return;
@@ -42,7 +42,7 @@ __global__ void det_stats_kernel(const float* __restrict__ post, const int32_t* 
   if (i == 0) {                                     // compute_det.py:83: max(score_list) (as rounded text values)
     float m = -INFINITY;
     for (long long u = 0; u < n; ++u) m = fmaxf(m, p[u * K]);
-    max_score[bk] = n > 0 ? (float)text_round6(m) : m;
+    max_score[bk] = n > 0 ? text_round6(m) : (double)m;     // the double Python parses back (compared in double)
   }
 }
 
@@ -52,7 +52,7 @@ __global__ void det_stats_kernel(const float* __restrict__ post, const int32_t* 
 using namespace wekws;
 
 extern "C" int wekws_det_stats(const float* d_post, const int32_t* d_lens, int64_t B, int64_t T, int K,
-                               const double* d_thresholds, int nthr, int window_shift, float* d_max_score,
+                               const double* d_thresholds, int nthr, int window_shift, double* d_max_score,
                                int32_t* d_triggers, void* stream) {
   WEKWS_REQUIRE(B >= 0 && T >= 0 && K >= 1 && nthr >= 1, "wekws_det_stats: bad sizes");
   WEKWS_REQUIRE(window_shift >= 1, "wekws_det_stats: window_shift must be >= 1 (got %d)", window_shift);

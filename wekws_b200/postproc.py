@@ -27,7 +27,7 @@ def det_thresholds(step: float = 0.01) -> torch.Tensor:
 def det_stats(post: torch.Tensor, lengths: Optional[torch.Tensor] = None, step: float = 0.01,
               window_shift: int = 50):
     """post (B, T, K) float32 CUDA posteriors, lengths (B,) valid frames.  Returns (thresholds (n,) float64 on the
-    host, max_score (B, K) float32, triggers (B, K, n) int32) -- see include/wekws_b200.h wekws_det_stats."""
+    host, max_score (B, K) float64, triggers (B, K, n) int32) -- see include/wekws_b200.h wekws_det_stats."""
     if not post.is_cuda:
         raise RuntimeError("wekws_b200.det_stats runs on CUDA only; got a CPU tensor (no CPU fallback)")
     if post.dim() != 3 or post.dtype != torch.float32:
@@ -37,7 +37,7 @@ def det_stats(post: torch.Tensor, lengths: Optional[torch.Tensor] = None, step: 
     thr = det_thresholds(step)
     d_thr = thr.to(post.device)
     lens = None if lengths is None else lengths.to(device=post.device, dtype=torch.int32).contiguous()
-    max_score = torch.empty(B, K, device=post.device, dtype=torch.float32)
+    max_score = torch.empty(B, K, device=post.device, dtype=torch.float64)
     triggers = torch.empty(B, K, thr.numel(), device=post.device, dtype=torch.int32)
     with torch.cuda.device(post.device):
         rc = _native.lib().wekws_det_stats(
