@@ -1,38 +1,46 @@
 #!/usr/bin/env python
 """Benchmark of the WeKws streaming KWS forward path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--no-extras]
 
-Workload (BASELINE.json configs[1]): the `mdtc` model (hidden 64, 1+4x4 DS-dilated blocks, k=5),
-80-dim features, B = 1024 concurrent streams per GPU, chunk T = 40 frames, streaming caches
-(B,64,244) carried from step to step.  A "step" is one pass of KWSModel.forward over one batch of
-B x T synthetic frames.  Metric: audio-hours/sec = frames/sec / 360000 (100 frames per second).
+Headline workload (BASELINE.json configs[1]): the `mdtc` model (hidden 64, 1+4x4 DS-dilated blocks, k=5),
+80-dim features, B = 1024 concurrent streams per GPU, chunk T = 40 frames, streaming caches (B,64,244)
+carried from step to step.  A "step" is one pass of KWSModel.forward over one batch of B x T synthetic
+frames.  Metric: audio-hours/sec = frames/sec / 360000 (100 frames per second).
 
-* `value`      whole-job throughput, inputs resident in HBM, device-timed (CUDA events), max over ranks.
-* `e2e`        same metric through the public Python surface (wekws_b200.KWSModel.forward) with the
-               step's features coming from pinned HOST memory (H2D) and its posteriors read back (D2H)
-               inside the timed region; the streaming cache stays on the device as it does in the
-               reference's own streaming loop (stream_kws_ctc.py:487).
-* `roofline`   dominant kernel conv_backbone_kernel<64>: algorithmic bytes per launch
-               (idim*4 + odim*4 + 2*cache_bytes_per_stream/T = 3447 B/frame) / mean
-               launch duration measured with CUDA events inside the timed region, against the measured
-               HBM copy bandwidth in MEASURED_PEAKS.json.
-* `cpu_baseline` the oracle port of the reference's PyTorch CPU path (oracle/kws_oracle.py) timed on the
-               host cores on a bounded sample of the same workload.
+* `value`      whole-job throughput of EXACTLY --steps steps after --warmup warm-ups, inputs resident in HBM,
+               device-timed (CUDA events) between barriers, max over ranks.
+* `e2e`        same metric through the public Python surface (wekws_b200.KWSModel.forward) with the step's
+               features coming from pinned HOST memory (H2D) and its posteriors read back (D2H) inside the
+               timed region; the streaming cache stays on the device as it does in the reference's own
+               streaming loop (stream_kws_ctc.py:487).  The e2e loop has its own length (`e2e.steps`): it
+               warms up until the per-step time is stable (>= 0.5 s) and then times >= 1 s, the same number of
+               steps on every rank, so a 20-step driver run does not time cold PCIe / first-touch effects.
+               Each rank binds itself (and therefore its pinned buffers, first touch) to the CPUs local to
+               its GPU before anything is allocated.
+* `roofline`   dominant kernel (mdtc_tc_kernel for the headline workload): algorithmic bytes per launch
+               (idim*4 + odim*4 + 2*cache_bytes_per_stream/T = 3447 B/frame) / mean launch
+               duration measured with CUDA events, against the measured HBM copy bandwidth in
+               MEASURED_PEAKS.json; plus the bf16 tensor-pipe figure for the tcgen05 kernels.
+* `cpu_baseline` / `--impl reference`: the oracle port of the reference's PyTorch CPU path
+               (oracle/kws_oracle.py, same ATen ops) on the host cores, run in a fresh process with the
+               full CPU affinity; thread count and sub-batch chosen by the median of 5 timed calls each.
+* `extra_workloads`: BASELINE configs[2..4] per GPU -- GRU B=512 T=1, tcn and ds_tcn B=1024 T=40, raw
+               PCM -> posterior 1250 x 1 s clips (p50 / p99 batch latency) -- each with its own value, e2e,
+               roofline and clock record, inside a bounded time budget.
 Multi-GPU: streams are independent -> each rank owns its own B streams ("weak" scaling), no collective
 on the data path; torch.distributed (NCCL) is used only for the barrier and the max-over-ranks time.
 Between timed steps the working set rotates over NSETS independent stream sets (> 126 MB L2).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
 import sys
 import threading
 import time
-
-import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -49,8 +57,42 @@ WORKLOADS = {
     # T = 98 frames per clip (16000 samples), every clip starts a stream (no cache carried)
     "pcm_e2e_1250x1s": ("mdtc", 1250, 98, 80),
 }
+EXTRAS = ["gru_b512_t1", "tcn_b1024_t40", "ds_tcn_b1024_t40", "pcm_e2e_1250x1s"]
 PCM_SAMPLES = 16000
 NSETS = 4
+METRIC = "audio-hours/sec KWS scoring (frames/sec / 360000)"
+DTYPE = "f32 I/O, bf16x3 tensor GEMMs (fp32 accumulate, ~2^-17; GRU and front-end: fp32 FMA)"
+
+
+# ------------------------------------------------------------------------------------------- host placement
+def bind_to_gpu_cpus(local_gpu):
+    """Pins this process to the CPUs local to its GPU (NUMA node of the PCIe root) BEFORE torch / CUDA allocate
+    anything, so the pinned staging buffers are first-touched on that node.  Returns (description, original
+    affinity) -- the CPU baseline runs in a child with the original affinity."""
+    try:
+        orig = os.sched_getaffinity(0)
+    except Exception:
+        return "affinity unavailable", None
+    try:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_gpu
+        if vis:
+            parts = [p.strip() for p in vis.split(",") if p.strip()]
+            if local_gpu < len(parts) and parts[local_gpu].isdigit():
+                idx = int(parts[local_gpu])
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (max(orig) // 64) + 1 if orig else 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1} & orig
+        if cpus and cpus != orig:
+            os.sched_setaffinity(0, cpus)
+            lo, hi = min(cpus), max(cpus)
+            return f"bound to the {len(cpus)} CPUs local to GPU {idx} (cpu {lo}..{hi})", orig
+        return "GPU-local CPU set == process CPU set (single NUMA domain)", orig
+    except Exception as e:  # no NVML / no permission: keep going unbound
+        return f"not bound ({type(e).__name__})", orig
 
 
 def measured_peaks():
@@ -58,8 +100,8 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return {}, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def algorithmic_bytes_per_frame(model, T, idim, odim=1):
@@ -87,6 +129,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -101,21 +144,23 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------- CPU reference arm
 def build_oracle_model(model_name, idim):
+    import torch
     from wekws_b200 import init_model, model_config, synth
     cfg = model_config(model_name, input_dim=idim)
     torch.manual_seed(777)
@@ -123,51 +168,373 @@ def build_oracle_model(model_name, idim):
     return cfg, m
 
 
-def cpu_reference_run(model_name, B, T, idim, steps, warmup, budget_s=20.0):
-    """The reference's CPU PyTorch path (oracle port, same ATen ops) on all host cores, on a bounded
-    sample of the workload: Bs streams x T frames per step, caches carried."""
+def cpu_reference_run(workload, steps, warmup, budget_s):
+    """The reference's CPU PyTorch path (oracle port, same ATen ops) on the host cores.  One step = the workload's
+    full per-GPU batch (B streams x T frames; raw-PCM workloads: per-clip kaldi-style Fbank + forward, the way the
+    reference does it), executed as ceil(B / sub) sub-batches; (threads, sub) = best median of 5 timed calls.
+    Runs `warmup` untimed and up to `steps` timed steps, stopping early (>= 3 steps) when budget_s is spent."""
+    import torch
     from oracle import kws_oracle as O
     from wekws_b200 import synth
-    ncpu = os.cpu_count() or 1
+    model_name, B, T, idim = WORKLOADS[workload]
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cfg, m = build_oracle_model(model_name, idim)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
-    Bs = min(B, 256)           # survey: best CPU throughput of this model is at B=256 (BASELINE.md section 3)
-    x = synth.features(Bs, T, idim, seed=4321)
     gru = cfg["backbone"]["type"] == "gru"
+    pcm_mode = workload.startswith("pcm_")
+    if pcm_mode:
+        pcm = synth.pcm_int16(B, PCM_SAMPLES, seed=1234).float()
+    else:
+        x = synth.features(B, T, idim, seed=4321)
 
-    def fresh_cache():
-        return torch.zeros(cfg["backbone"]["num_layers"], Bs, cfg["hidden_dim"]) if gru else None
+    def make_step(sub):
+        slices = [(s, min(B, s + sub)) for s in range(0, B, sub)]
+        caches = [torch.zeros(cfg["backbone"]["num_layers"], e - s, cfg["hidden_dim"]) if gru else None
+                  for s, e in slices]
 
-    # give the reference its best shot: probe thread counts (all cores oversubscribes ATen's small convs)
-    cand = sorted({n for n in (1, 4, 8, 16, 32, 64, ncpu) if n <= ncpu})
-    best, cores = None, ncpu
-    for n in cand:
-        torch.set_num_threads(n)
-        c = fresh_cache()
-        _, c = O.kws_forward(sd, cfg, x, c)
-        t0 = time.perf_counter()
-        _, c = O.kws_forward(sd, cfg, x, c)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, cores = dt, n
+        def step():
+            for i, (s, e) in enumerate(slices):
+                if pcm_mode:      # per-clip Fbank (kaldi.fbank is single-waveform, kaldi.py:135-137), batched forward
+                    f = torch.stack([O.fbank(pcm[b]) for b in range(s, e)])
+                    O.kws_forward(sd, cfg, f, None)
+                else:
+                    _, caches[i] = O.kws_forward(sd, cfg, x[s:e], caches[i])
+        return step
+
+    def median_time(fn, n):
+        fn()
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return statistics.median(ts)
+
+    # probe on a slice of the batch: threads x sub-batch, median of 5 timed calls each, bounded in time
+    threads = [n for n in dict.fromkeys((16, 32, 8, 64, 4, ncpu, 1)) if n <= ncpu]   # likely winners first (time-bounded)
+    subs = sorted({s for s in (64, 256, B) if s <= B}) if not pcm_mode else [min(B, 125)]
+    best = None
+    t_probe = time.perf_counter()
+    for sub in subs:
+        probe_b = min(B, sub)
+        xs = None if pcm_mode else x[:probe_b]
+        for n in threads:
+            torch.set_num_threads(n)
+            c0 = [torch.zeros(cfg["backbone"]["num_layers"], probe_b, cfg["hidden_dim"]) if gru else None]
+
+            def call():
+                if pcm_mode:
+                    f = torch.stack([O.fbank(pcm[b]) for b in range(probe_b)])
+                    O.kws_forward(sd, cfg, f, None)
+                else:
+                    _, c0[0] = O.kws_forward(sd, cfg, xs, c0[0])
+            dt = median_time(call, 5) / probe_b           # seconds per stream-chunk
+            if best is None or dt < best[0]:
+                best = (dt, n, sub)
+            if time.perf_counter() - t_probe > 0.45 * budget_s:
+                break
+    _, cores, sub = best
     torch.set_num_threads(cores)
-    cache = fresh_cache()
+    step = make_step(sub)
     for _ in range(warmup):
-        _, cache = O.kws_forward(sd, cfg, x, cache)
+        step()
     times = []
     t_start = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        _, cache = O.kws_forward(sd, cfg, x, cache)
+        step()
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
     total = sum(times)
-    fps = Bs * T * len(times) / total
+    fps = B * T * len(times) / total
     return {"value": fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "cores": cores, "kind": "port",
-            "frames_per_sec": fps, "ms_per_step": 1e3 * total / len(times), "steps": len(times),
-            "sample": f"oracle port (torch CPU, best of {cand} threads = {cores}; host has {ncpu}) of {model_name}: "
-                      f"{Bs} streams x {T} frames per step, cache carried, {len(times)} steps"}
+            "frames_per_sec": fps, "ms_per_step": 1e3 * total / len(times), "steps": len(times), "warmup": warmup,
+            "sample": f"oracle port (torch CPU) of {workload}: {len(times)} steps of the full per-GPU batch "
+                      f"({B} x {T} frames, as sub-batches of {sub}), state carried; threads/sub-batch = best median "
+                      f"of 5 calls over {threads} x {subs} -> {cores} threads; host exposes {ncpu} CPUs"}
+
+
+def reference_line(args, config, r):
+    return {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "audio-hours/s", "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "frames_per_sec": r["frames_per_sec"],
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def workload_config(workload, gpus):
+    model_name, B, T, idim = WORKLOADS[workload]
+    cfg = {"workload": f"{model_name}: {B} streams/GPU x {T}-frame chunks, {idim}-dim features, cache carried",
+           "model_cfg": model_name, "streams_per_gpu": B, "chunk_frames": T, "feature_dim": idim,
+           "global_streams": B * max(gpus, 1), "parallelism": f"streams sharded x{max(gpus, 1)} (no collective)",
+           "l2": f"working set rotates over {NSETS} independent stream sets (> 126 MB L2 for the conv models)"}
+    if workload.startswith("pcm_"):
+        cfg["workload"] = (f"raw int16 PCM -> Fbank -> {model_name}: {B} one-second clips/GPU "
+                           f"({T} frames each), start of stream")
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------- our arm
+class Runner:
+    def __init__(self, dev, rank, world, dist):
+        self.dev, self.rank, self.world, self.dist = dev, rank, world, dist
+
+    def barrier(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(self, v, op="max"):
+        import torch
+        t = torch.tensor([float(v)], device=self.dev, dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def run(self, workload, steps, warmup, min_region_s=0.0):
+        """value / latency / e2e / roofline of one workload.  steps, warmup: the device-resident timed loop (exactly
+        as given when min_region_s == 0; extras pass min_region_s to size the loop by time instead)."""
+        import torch
+        from wekws_b200 import _native, init_model, model_config, synth
+        dev, rank, world = self.dev, self.rank, self.world
+        model_name, B, T, idim = WORKLOADS[workload]
+        cfg = model_config(model_name, input_dim=idim)
+        torch.manual_seed(777)
+        model = synth.randomize_(init_model(cfg), seed=777).eval().to(dev)
+        gru = model_name == "gru"
+        cshape = (2, B, 128) if gru else (B, model.hdim, model.backbone.padding)
+        pcm_mode = workload.startswith("pcm_")
+        if pcm_mode:
+            from wekws_b200 import Fbank
+            fb = Fbank(idim)
+            pcm = [synth.pcm_int16(B, PCM_SAMPLES, seed=1234 + rank * 17 + s).to(dev) for s in range(NSETS)]
+            feat_buf = torch.empty(B, T, idim, device=dev)
+            feats = [feat_buf] * NSETS
+            caches = [None] * NSETS
+        else:
+            feats = [synth.features(B, T, idim, seed=4321 + rank * 17 + s).to(dev) for s in range(NSETS)]
+            caches = [torch.zeros(cshape, device=dev) for _ in range(NSETS)]
+
+        def step(i):
+            s = i % NSETS
+            if pcm_mode:
+                model(fb(pcm[s], out=feat_buf))
+            else:
+                _, caches[s] = model(feats[s], caches[s])
+
+        # ---------------- device-resident throughput (`value`) ------------------------------------------------
+        for i in range(max(warmup, 3)):
+            step(i)
+        self.barrier()
+        if min_region_s > 0:          # extras: size the loop by time (same count on every rank)
+            t0 = time.perf_counter()
+            for i in range(20):
+                step(i)
+            torch.cuda.synchronize()
+            per = (time.perf_counter() - t0) / 20
+            steps = int(self.reduce(max(20, min(20000, math.ceil(min_region_s / max(per, 1e-6))))))
+            self.barrier()
+        sampler = ClockSampler(dev.index).start() if rank == 0 else None
+        n0 = _native.launch_count()
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin.record()
+        for i in range(steps):
+            step(i)
+        t_end.record()
+        self.barrier()
+        launches = _native.launch_count() - n0
+        total_ms = self.reduce(t_begin.elapsed_time(t_end))
+        fps = B * T * steps * world / (total_ms * 1e-3)
+        # per-launch durations (roofline, p50/p99) from a separate pass: bracketing every step with events costs
+        # more host time than a 10 us kernel takes, so it stays out of the timed region
+        nlat = 200
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nlat)]
+        for i in range(nlat):
+            ev[i][0].record()
+            step(i)
+            ev[i][1].record()
+        self.barrier()
+        per_launch_ms = [a.elapsed_time(b) for a, b in ev]
+
+        # ---------------- end to end through the public API with host buffers (`e2e`) --------------------------
+        src = pcm if pcm_mode else feats
+        h_in = [t.cpu().pin_memory() for t in src]
+        h_out = [torch.empty(B, T, model.odim).pin_memory() for _ in range(2)]
+        d_in = [torch.empty_like(src[0]) for _ in range(2)]
+        copy_stream, main_stream = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_run(nsteps):
+            # H2D of step i+1 overlaps the kernel of step i (separate copy stream, double buffered);
+            # every step's posteriors are copied back to pinned host memory
+            with torch.cuda.stream(copy_stream):
+                d_in[0].copy_(h_in[0], non_blocking=True)
+                in_ready[0].record(copy_stream)
+            for i in range(nsteps):
+                b, s = i & 1, i % NSETS
+                if i + 1 < nsteps:
+                    nb = (i + 1) & 1
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(in_free[nb])
+                        d_in[nb].copy_(h_in[(i + 1) % NSETS], non_blocking=True)
+                        in_ready[nb].record(copy_stream)
+                main_stream.wait_event(in_ready[b])
+                if pcm_mode:
+                    y, _ = model(fb(d_in[b], out=feat_buf))
+                else:
+                    y, caches[s] = model(d_in[b], caches[s])
+                in_free[b].record(main_stream)
+                h_out[b].copy_(y, non_blocking=True)
+            main_stream.synchronize()
+
+        def e2e_timed(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            e2e_run(n)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        # warm-up until the per-step time is stable (two consecutive ~0.1 s chunks within 5 %) and >= 0.5 s have
+        # passed (at most 3 s): first-touch of the pinned buffers, PCIe link power state, clocks
+        per, t_w = e2e_timed(8), time.perf_counter()
+        while True:
+            n = max(8, min(4000, int(100.0 / max(per, 1e-3))))
+            new = e2e_timed(n)
+            stable = abs(new - per) <= 0.05 * per
+            per = new
+            el = time.perf_counter() - t_w
+            if (stable and el >= 0.5) or el >= 3.0:
+                break
+        e2e_steps = int(self.reduce(max(16, min(40000, math.ceil(1000.0 / max(per, 1e-3))))))
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_run(e2e_steps)
+        e1.record()
+        self.barrier()
+        e2e_ms = self.reduce(e0.elapsed_time(e1))
+        e2e_fps = B * T * e2e_steps * world / (e2e_ms * 1e-3)
+        # serialized per-batch completion latency through the host API (H2D -> kernels -> D2H, one batch in flight)
+        e2e_lat = None
+        if pcm_mode or gru:
+            ls = []
+            for i in range(100):
+                a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                d_in[0].copy_(h_in[i % NSETS], non_blocking=True)
+                if pcm_mode:
+                    y, _ = model(fb(d_in[0], out=feat_buf))
+                else:
+                    y, caches[0] = model(d_in[0], caches[0])
+                h_out[0].copy_(y, non_blocking=True)
+                b2.record()
+                torch.cuda.synchronize()
+                ls.append(a.elapsed_time(b2))
+            ls.sort()
+            e2e_lat = {"p50_ms": ls[len(ls) // 2], "p99_ms": ls[min(len(ls) - 1, int(0.99 * len(ls)))],
+                       "what": "one batch in flight: pinned H2D + kernels + D2H of the posteriors"}
+        clocks = sampler.stop() if sampler is not None else None
+
+        # ---------------- single-stream chunk latency (BASELINE configs[0] shape on the GPU) -------------------
+        lat = None
+        if rank == 0 and not pcm_mode:
+            x1 = synth.features(1, T, idim, seed=1).to(dev)
+            c1 = torch.zeros((2, 1, 128) if gru else (1, model.hdim, model.backbone.padding), device=dev)
+            for _ in range(20):
+                _, c1 = model(x1, c1)
+            torch.cuda.synchronize()
+            ls = []
+            for _ in range(200):
+                a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _, c1 = model(x1, c1)
+                b2.record()
+                torch.cuda.synchronize()
+                ls.append(a.elapsed_time(b2))
+            lat = statistics.median(ls)
+        if rank != 0:
+            return None
+
+        peaks, peak, peak_src = measured_peaks()
+        bpf = algorithmic_bytes_per_frame(model_name, T, idim, model.odim)
+        if pcm_mode:   # PCM in + posteriors out + the new cache written once (no cache read at start of stream)
+            bpf = PCM_SAMPLES * 2.0 / T + model.odim * 4 + (64 * 244 * 4) / T
+        launch_ms = statistics.mean(per_launch_ms)
+        srt = sorted(per_launch_ms)
+        p99_ms = srt[min(len(srt) - 1, int(0.99 * len(srt)))]
+        achieved = bpf * B * T / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get(workload, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        tc = bool(model.uses_tensor_cores(T))
+        kname = "gru_kernel" if gru else ({"tcn": "tcn_tc_kernel", "ds_tcn": "dstcn_tc_kernel"}.get(
+            model_name, "mdtc_tc_kernel") if tc else "conv_backbone_kernel")
+        flop_per_frame = {"mdtc": 299776, "tcn": 272512, "ds_tcn": 582144, "gru": 413952}.get(model_name)
+        res = {
+            "workload": workload, "config": workload_config(workload, world),
+            "value": fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "frames_per_sec": fps, "steps": steps,
+            "ms_per_step": total_ms / steps,
+            "p50_step_latency_ms": statistics.median(per_launch_ms), "p99_step_latency_ms": p99_ms,
+            "p50_chunk_latency_ms_1stream": lat, "clocks": clocks,
+            "e2e": {"value": e2e_fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "frames_per_sec": e2e_fps,
+                    "h2d_bytes_per_step": (B * PCM_SAMPLES * 2) if pcm_mode else (B * T * idim * 4),
+                    "d2h_bytes_per_step": B * T * model.odim * 4, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps, "batch_latency": e2e_lat,
+                    "api": "wekws_b200.KWSModel.forward(feats, cache)" + (" after wekws_b200.Fbank(pcm)" if pcm_mode else "")
+                           + "; pinned host input in, posteriors out, H2D double-buffered on a copy stream; "
+                             "own step count: warm-up until stable (>= 0.5 s), then >= 1 s timed"},
+            "gpu_launches": launches, "tensor_cores": tc,
+            "roofline": {"kernel": ("fbank_kernel + " if pcm_mode else "") + kname, "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src + ", burst", "traffic": traffic,
+                         "algorithmic_bytes_per_frame": bpf, "launch_ms": launch_ms,
+                         "fp32_tflops": (flop_per_frame * B * T / (launch_ms * 1e-3) / 1e12) if flop_per_frame else None,
+                         "note": "HBM fraction as SURVEY 8d asks; at fp32 parity the fused backbones are bound by "
+                                 "instruction issue / shared memory / the tensor pipe (DESIGN.md section 4)"},
+        }
+        # SURVEY 8d second figure for the tensor-core kernels: bf16 tensor-pipe utilisation = dense GEMM FLOP/frame
+        # x 3 passes of the bf16x3 split / measured bf16 peak (MEASURED_PEAKS.json)
+        dense = {"mdtc": 34 * 2 * 64 * 64 + 2 * 80 * 64, "tcn": 32 * 2 * 64 * 64 + 2 * 80 * 64,
+                 "ds_tcn": 4 * 2 * 256 * 256 + 2 * 80 * 256}.get(model_name)
+        bf16_peak = float(peaks.get("bf16_tflops", 0) or 0)
+        if dense and tc and not pcm_mode and bf16_peak:
+            tf = 3.0 * dense * B * T / (launch_ms * 1e-3) / 1e12
+            res["roofline"]["tensor_pipe"] = {"achieved_bf16_tflops": tf, "peak_bf16_tflops": bf16_peak,
+                                              "frac": tf / bf16_peak, "passes": 3}
+        return res
+
+
+def cpu_baseline_subprocess(workload, orig_affinity, budget_s):
+    """The CPU leg in a fresh process with the full CPU set (this process is pinned to its GPU's NUMA node)."""
+    cur = None
+    try:
+        if orig_affinity:
+            cur = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, orig_affinity)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                              "--steps", "40", "--warmup", "2", "--cpu-budget", str(budget_s)],
+                             capture_output=True, text=True, timeout=600,
+                             env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:
+        return {"value": None, "unit": "audio-hours/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+    finally:
+        if cur:
+            os.sched_setaffinity(0, cur)
 
 
 def main():
@@ -178,32 +545,23 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mdtc_b1024_t40", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra_workloads (BASELINE configs[2..4])")
+    ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of timed CPU work for --impl reference")
     args = ap.parse_args()
-    model_name, B, T, idim = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{model_name}: {B} streams/GPU x {T}-frame chunks, {idim}-dim features, cache carried",
-              "model_cfg": model_name, "streams_per_gpu": B, "chunk_frames": T, "feature_dim": idim,
-              "global_streams": B * max(args.gpus, 1), "parallelism": f"streams sharded x{max(args.gpus, 1)} (no collective)",
-              "l2": f"working set rotates over {NSETS} independent stream sets (~{NSETS * 77} MB) > 126 MB L2"}
+    config = workload_config(args.workload, args.gpus)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = min(args.steps, 50)
-        r = cpu_reference_run(model_name, B, T, idim, steps, max(min(args.warmup, 3), 1), budget_s=60.0)
-        line = {"impl": "reference", "metric": "audio-hours/sec KWS scoring (frames/sec / 360000)",
-                "value": r["value"], "unit": "audio-hours/s", "n_gpus": args.gpus, "steps": r["steps"],
-                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "frames_per_sec": r["frames_per_sec"],
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+        r = cpu_reference_run(args.workload, args.steps, args.warmup, budget_s=args.cpu_budget)
+        print(json.dumps(reference_line(args, config, r)))
         return 0
 
+    placement, orig_aff = bind_to_gpu_cpus(local)
+    import torch
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (B200)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -212,205 +570,30 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    from wekws_b200 import _native, init_model, model_config, synth
-    cfg = model_config(model_name, input_dim=idim)
-    torch.manual_seed(777)
-    model = synth.randomize_(init_model(cfg), seed=777).eval().to(dev)
-    gru = model_name == "gru"
-    cshape = (2, B, 128) if gru else (B, model.hdim, model.backbone.padding)
-    pcm_mode = args.workload.startswith("pcm_")
-    if pcm_mode:
-        from wekws_b200 import Fbank
-        fb = Fbank(idim)
-        pcm = [synth.pcm_int16(B, PCM_SAMPLES, seed=1234 + rank * 17 + s).to(dev) for s in range(NSETS)]
-        feat_buf = torch.empty(B, T, idim, device=dev)
-        feats = [feat_buf] * NSETS
-        caches = [None] * NSETS
-        config["workload"] = (f"raw int16 PCM -> Fbank -> {model_name}: {B} one-second clips/GPU "
-                              f"({T} frames each), start of stream")
-    else:
-        feats = [synth.features(B, T, idim, seed=4321 + rank * 17 + s).to(dev) for s in range(NSETS)]
-        caches = [torch.zeros(cshape, device=dev) for _ in range(NSETS)]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput (`value`) + per-launch durations (roofline) ----------
-    def step(i):
-        s = i % NSETS
-        if pcm_mode:
-            model(fb(pcm[s], out=feat_buf))
-        else:
-            _, caches[s] = model(feats[s], caches[s])
-
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    n0 = _native.launch_count()
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_begin.record()
-    for i in range(args.steps):
-        step(i)
-    t_end.record()
-    barrier()
-    launches = _native.launch_count() - n0
-    total_ms = t_begin.elapsed_time(t_end)
-    # per-launch durations (roofline, p50/p99) from a separate short pass: bracketing every step with
-    # events costs more host time than a 20 us kernel takes, so it stays out of the timed region
-    nlat = min(args.steps, 200)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nlat)]
-    for i in range(nlat):
-        ev[i][0].record()
-        step(i)
-        ev[i][1].record()
-    barrier()
-    per_launch_ms = [a.elapsed_time(b) for a, b in ev]
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    frames_total = B * T * args.steps * world
-    fps = frames_total / (total_ms_max * 1e-3)
-
-    # ---------------- end to end through the public API with host buffers (`e2e`) ----------------------
-    h_feats = [(p if pcm_mode else f).cpu().pin_memory() for p, f in zip(pcm if pcm_mode else feats, feats)]
-    h_out = [torch.empty(B, T, model.odim).pin_memory() for _ in range(2)]
-    d_in = [torch.empty_like(pcm[0] if pcm_mode else feats[0]) for _ in range(2)]
-    copy_stream, main_stream = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
-    in_ready = [torch.cuda.Event() for _ in range(2)]
-    in_free = [torch.cuda.Event() for _ in range(2)]
-
-    def e2e_run(nsteps):
-        # H2D of step i+1 overlaps the kernel of step i (separate copy stream, double buffered);
-        # every step's posteriors are copied back to pinned host memory
-        with torch.cuda.stream(copy_stream):
-            d_in[0].copy_(h_feats[0], non_blocking=True)
-            in_ready[0].record(copy_stream)
-        for i in range(nsteps):
-            b, s = i & 1, i % NSETS
-            if i + 1 < nsteps:
-                nb = (i + 1) & 1
-                with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(in_free[nb])
-                    d_in[nb].copy_(h_feats[(i + 1) % NSETS], non_blocking=True)
-                    in_ready[nb].record(copy_stream)
-            main_stream.wait_event(in_ready[b])
-            if pcm_mode:
-                y, _ = model(fb(d_in[b], out=feat_buf))
-            else:
-                y, caches[s] = model(d_in[b], caches[s])
-            in_free[b].record(main_stream)
-            h_out[b].copy_(y, non_blocking=True)
-        main_stream.synchronize()
-
-    e2e_steps = args.steps
-    e2e_run(max(args.warmup, 3))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    e0.record()
-    e2e_run(e2e_steps)
-    e1.record()
-    barrier()
-    # the sampler spans both timed loops (device-resident + end to end): a 2000-step GRU loop is over in 40 ms,
-    # shorter than one nvidia-smi sampling period
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    e2e_wall_ms = (time.perf_counter() - wall0) * 1e3
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_fps = B * T * e2e_steps * world / (float(t.item()) * 1e-3)
-
-    # ---------------- single-stream chunk latency (BASELINE configs[0] shape on the GPU) ---------------
-    lat = None
-    if rank == 0:
-        x1 = synth.features(1, T, idim, seed=1).to(dev)
-        c1 = torch.zeros((2, 1, 128) if gru else (1, model.hdim, model.backbone.padding), device=dev)
-        for _ in range(20):
-            _, c1 = model(x1, c1)
-        torch.cuda.synchronize()
-        ls = []
-        for _ in range(200):
-            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            _, c1 = model(x1, c1)
-            b2.record()
-            torch.cuda.synchronize()
-            ls.append(a.elapsed_time(b2))
-        lat = statistics.median(ls)
-
+    runner = Runner(dev, rank, world, dist)
+    main_res = runner.run(args.workload, args.steps, args.warmup)
+    extras = []
+    if not args.no_extras and args.workload == "mdtc_b1024_t40":
+        for w in EXTRAS:
+            r = runner.run(w, steps=0, warmup=5, min_region_s=0.25)
+            if r is not None:
+                extras.append(r)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peaks()
-    bpf = algorithmic_bytes_per_frame(model_name, T, idim, model.odim)
-    if pcm_mode:   # PCM in + posteriors out + the new cache written once (no cache read at start of stream)
-        bpf = PCM_SAMPLES * 2.0 / T + model.odim * 4 + (64 * 244 * 4) / T
-    launch_ms = statistics.mean(per_launch_ms)
-    srt = sorted(per_launch_ms)
-    p99_ms = srt[min(len(srt) - 1, int(0.99 * len(srt)))]
-    achieved = bpf * B * T / (launch_ms * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "dominant_kernel.json")
-    if os.path.exists(prof):
-        try:
-            with open(prof) as f:
-                traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    flop_per_frame = {"mdtc": 299776, "tcn": 272512, "ds_tcn": 582144, "gru": 413952}.get(model_name)
-    line = {
-        "metric": "audio-hours/sec KWS scoring (frames/sec / 360000)",
-        "value": fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-        "frames_per_sec": fps,
-        "p50_step_latency_ms": statistics.median(per_launch_ms), "p99_step_latency_ms": p99_ms,
-        "p50_chunk_latency_ms_1stream": lat,
-        "clocks": clocks,
-        "e2e": {"value": e2e_fps / FRAMES_PER_HOUR, "unit": "audio-hours/s", "frames_per_sec": e2e_fps,
-                "h2d_bytes_per_step": (B * PCM_SAMPLES * 2) if pcm_mode else (B * T * idim * 4),
-                "d2h_bytes_per_step": B * T * model.odim * 4,
-                "ms_per_step": float(t.item()) / e2e_steps,
-                "api": "wekws_b200.KWSModel.forward(feats, cache); pinned host feats in, posteriors out, "
-                       "H2D double-buffered on a copy stream"},
-        "gpu_launches": launches,
-        "tensor_cores": bool(model.uses_tensor_cores(T)),
-        "roofline": {"kernel": ("fbank_kernel + " if pcm_mode else "") + (({"tcn": "tcn_tc_kernel", "ds_tcn": "dstcn_tc_kernel"}.get(model_name, "mdtc_tc_kernel") if model.uses_tensor_cores(T) else "conv_backbone_kernel") if not gru else "gru_kernel"), "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src + ", burst", "traffic": traffic,
-                     "algorithmic_bytes_per_frame": bpf, "launch_ms": launch_ms,
-                     "fp32_tflops": (flop_per_frame * B * T / (launch_ms * 1e-3) / 1e12) if flop_per_frame else None,
-                     "note": "HBM fraction as SURVEY 8d asks; the fused backbone is instruction/shared-memory bound "
-                             "(DESIGN.md section 4)"},
-    }
-    # SURVEY 8d second figure for the tensor-core kernels: bf16 tensor-pipe utilisation = dense GEMM FLOP/frame x 3
-    # passes of the bf16x3 split / measured bf16 peak (MEASURED_PEAKS.json); informational, never fatal
-    try:
-        dense = {"mdtc": 34 * 2 * 64 * 64 + 2 * 80 * 64, "tcn": 32 * 2 * 64 * 64 + 2 * 80 * 64,
-                 "ds_tcn": 4 * 2 * 256 * 256 + 2 * 80 * 256}.get(model_name)
-        if dense and line["tensor_cores"] and not pcm_mode:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                pk = json.load(f)
-            bf16_peak = float(pk.get("bf16_tflops", pk.get("bf16_tflops_burst", 0)) or 0)
-            tf = 3.0 * dense * B * T / (launch_ms * 1e-3) / 1e12
-            line["roofline"]["tensor_pipe"] = {"achieved_bf16_tflops": tf, "peak_bf16_tflops": bf16_peak or None,
-                                               "frac": (tf / bf16_peak) if bf16_peak else None, "passes": 3}
-    except Exception:
-        pass
+    line = {"metric": METRIC, "value": main_res["value"], "unit": "audio-hours/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": dict(config, host_placement=placement)}
+    for k in ("frames_per_sec", "p50_step_latency_ms", "p99_step_latency_ms", "p50_chunk_latency_ms_1stream", "clocks",
+              "e2e", "gpu_launches", "tensor_cores", "roofline"):
+        line[k] = main_res[k]
+    if extras:
+        line["extra_workloads"] = extras
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(model_name, B, T, idim, steps=40, warmup=2, budget_s=15.0)
-        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, orig_aff, budget_s=15.0)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define WEKWS_B200_ABI_VERSION 2   /* 2: + wekws_fbank_set_mfcc, wekws_fbank_feature_dim, wekws_det_stats */
+#define WEKWS_B200_ABI_VERSION 3   /* 2: + wekws_fbank_set_mfcc, wekws_fbank_feature_dim, wekws_det_stats; 3: det max_score is double */
 
 #if defined(__GNUC__)
 #define WEKWS_API __attribute__((visibility("default")))

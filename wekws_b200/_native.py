@@ -17,7 +17,7 @@ BACKBONE_MDTC, BACKBONE_TCN, BACKBONE_DSTCN, BACKBONE_GRU = 0, 1, 2, 3
 ACT_IDENTITY, ACT_SIGMOID = 0, 1
 PCM_S16, PCM_F32 = 0, 1
 FWD_SOFTMAX = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FbankConfig(C.Structure):
