@@ -60,7 +60,11 @@ typedef enum {
   WEKWS_BACKBONE_MDTC = 0,    /* wekws/model/mdtc.py  MDTC                             */
   WEKWS_BACKBONE_TCN = 1,     /* wekws/model/tcn.py   TCN(block_class=CnnBlock)        */
   WEKWS_BACKBONE_DSTCN = 2,   /* wekws/model/tcn.py   TCN(block_class=DsCnnBlock)      */
-  WEKWS_BACKBONE_GRU = 3      /* torch.nn.GRU, kws_model.py:128-133                    */
+  WEKWS_BACKBONE_GRU = 3,     /* torch.nn.GRU, kws_model.py:128-133                    */
+  WEKWS_BACKBONE_FSMN = 4     /* wekws/model/fsmn.py FSMN (preprocessing none, classifier identity,
+                                 kws_model.py:158-170,121-122,191): tensors backbone.in_linear{1,2}.linear.*,
+                                 backbone.fsmn.{l}.{0.linear.weight,1.conv_left.weight,1.conv_right.weight,
+                                 2.linear.*}, backbone.out_linear{1,2}.linear.*                    */
 } wekws_backbone;
 
 typedef enum { WEKWS_ACT_IDENTITY = 0, WEKWS_ACT_SIGMOID = 1 } wekws_activation;
@@ -133,11 +137,15 @@ typedef struct {
   int32_t kernel_size;     /* conv taps (mdtc 5, tcn 8)                                */
   int32_t activation;      /* wekws_activation                                         */
   int32_t norm_var;        /* cmvn.norm_var; used when global_cmvn.* tensors are set   */
+  /* FSMN only (fsmn_ctc.yaml:40-52); num_layers = FSMN layers; the memory blocks always use strides 1,1 as the
+   * reference builds them (fsmn.py:384-391); cache (B, proj_dim, left_order - 1 + right_order, num_layers)  */
+  int32_t fsmn_input_affine_dim, fsmn_linear_dim, fsmn_proj_dim;
+  int32_t fsmn_left_order, fsmn_right_order, fsmn_output_affine_dim;
 } wekws_model_config;
 
 WEKWS_API int wekws_model_create(const wekws_model_config* cfg, wekws_model** out);
 WEKWS_API void wekws_model_destroy(wekws_model* m);
-/* Total cache columns == backbone.padding (mdtc 244, tcn/ds_tcn 105); 0 for GRU.   */
+/* Total cache columns == backbone.padding (mdtc 244, tcn/ds_tcn 105; FSMN lorder-1+rorder); 0 for GRU. */
 WEKWS_API int wekws_model_padding(const wekws_model* m);
 /* name: reference state_dict key, e.g. "backbone.blocks.0.res_blocks.1.bn1.running_var".
  * Data is copied.  num_batches_tracked entries may be skipped.                      */
@@ -159,7 +167,7 @@ WEKWS_API int64_t wekws_model_packed_floats(const wekws_model* m, int which /*0 
 WEKWS_API int wekws_model_packed_copy(const wekws_model* m, int which, float* h_dst, int64_t capacity);
 
 /* d_feats (B,T,idim); d_in_cache NULL (start of stream == zeros) or
- * conv: (B,hdim,padding)  GRU: (num_layers,B,hdim); d_out (B,T,odim);
+ * conv: (B,hdim,padding)  GRU: (num_layers,B,hdim)  FSMN: (B,proj_dim,padding,num_layers); d_out (B,T,odim);
  * d_out_cache same shape as the cache; it may be the SAME buffer as d_in_cache (in-place
  * streaming update: every slice is read before it is overwritten) or a disjoint one, not a
  * partially overlapping one.                                                       */
@@ -178,6 +186,14 @@ WEKWS_API int wekws_model_forward(wekws_model* m, const float* d_feats, const fl
 WEKWS_API int wekws_det_stats(const float* d_post, const int32_t* d_lens, int64_t B, int64_t T, int K,
                     const double* d_thresholds, int nthr, int window_shift, double* d_max_score,
                     int32_t* d_triggers, void* stream);
+
+/* Context expansion + frame skipping of the FSMN / CTC recipes: wekws/dataset/processor.py:267-312
+ * (batched twin wekws/dataset/init_dataset.py:24-68).  d_feats (B,T,D); d_lens NULL = all T frames valid;
+ * d_out (B, out_frames, D*(left+right+1)): row i of stream b = concat(feats[max(i*skip+k-left, 0)], k = 0..left+right)
+ * for i < wekws_context_expand_frames(lens[b], right, skip), zeros after.                                      */
+WEKWS_API int64_t wekws_context_expand_frames(int64_t num_frames, int right, int skip);
+WEKWS_API int wekws_context_expand(const float* d_feats, const int32_t* d_lens, int64_t B, int64_t T, int D, int left,
+                         int right, int skip, float* d_out, int64_t out_frames, void* stream);
 
 /* Raw PCM -> posteriors: Fbank(+CMVN from the model's global_cmvn.* if set) -> model.
  * d_feat_scratch: (B, frames, idim) floats of workspace owned by the caller.        */

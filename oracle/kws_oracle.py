@@ -416,3 +416,25 @@ def det_curve_text(thresholds, max_score, triggers, kinds, durations, k: int) ->
             false_alarm_per_hour = num_false_alarm / (filler_duration / 3600.0)
         lines.append('{:.6f} {:.6f} {:.6f}\n'.format(threshold, false_alarm_per_hour, false_reject_rate))
     return ''.join(lines)
+
+
+# ---------------------------------------------------------------------------- input transforms of the CTC recipes
+def context_expansion(feats: Tensor, left: int = 1, right: int = 1) -> Tensor:
+    """wekws/dataset/processor.py:267-296 for one utterance (T, D) -> (T - right, D * (left + right + 1)): roll-based
+    stacking of lags -left..right, first frame replicated into the left margin (:288-292), last `right` frames dropped
+    (:294).  Pinned by tests/golden/context.npz (made by running the reference function itself)."""
+    T, D = feats.shape
+    out = torch.zeros(T, D * (left + right + 1), dtype=torch.float32)
+    index = 0
+    for lag in range(-left, right + 1):
+        out[:, index:index + D] = torch.roll(feats, -lag, 0)
+        index += D
+    for idx in range(left):
+        for cpx in range(left - idx):
+            out[idx, cpx * D:(cpx + 1) * D] = out[left, :D]
+    return out[:T - right]
+
+
+def frame_skip(feats: Tensor, skip_rate: int = 1) -> Tensor:
+    """wekws/dataset/processor.py:299-312."""
+    return feats[::skip_rate, :]

@@ -151,3 +151,12 @@ def test_oracle_det_stats_pinned_to_reference_compute_det():
         thr, ms, tr = O.det_stats(post, lens, step, int(ws))
         for k in range(post.shape[2]):
             assert O.det_curve_text(thr, ms, tr, kinds, durs, k) == str(g[f"stats_{si}_{k}"]), (si, k)
+
+
+def test_oracle_context_expansion_pinned_to_reference_processor():
+    """O.context_expansion / O.frame_skip == the reference's own processor functions (tests/golden/context.npz, made by
+    oracle/make_context_golden.py running wekws/dataset/processor.py:267-312), bit for bit."""
+    g = golden("context")
+    for i, (T, D, left, right, skip) in enumerate(g["cases"].tolist()):
+        y = O.frame_skip(O.context_expansion(torch.from_numpy(g[f"x{i}"]), left, right), skip)
+        assert torch.equal(y, torch.from_numpy(g[f"y{i}"])), i

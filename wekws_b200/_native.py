@@ -10,10 +10,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwekws_b200.so")
+# WEKWS_B200_LIB: development override (A/B of two builds of the same ABI); the product default is the in-tree library
+LIB_PATH = os.environ.get("WEKWS_B200_LIB") or os.path.join(_HERE, "libwekws_b200.so")
 
 # enums (include/wekws_b200.h)
-BACKBONE_MDTC, BACKBONE_TCN, BACKBONE_DSTCN, BACKBONE_GRU = 0, 1, 2, 3
+BACKBONE_MDTC, BACKBONE_TCN, BACKBONE_DSTCN, BACKBONE_GRU, BACKBONE_FSMN = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_SIGMOID = 0, 1
 PCM_S16, PCM_F32 = 0, 1
 FWD_SOFTMAX = 1
@@ -29,7 +30,10 @@ class FbankConfig(C.Structure):
 class ModelConfig(C.Structure):
     _fields_ = [("backbone", C.c_int32), ("idim", C.c_int32), ("hdim", C.c_int32), ("odim", C.c_int32),
                 ("num_layers", C.c_int32), ("num_stack", C.c_int32), ("stack_size", C.c_int32),
-                ("kernel_size", C.c_int32), ("activation", C.c_int32), ("norm_var", C.c_int32)]
+                ("kernel_size", C.c_int32), ("activation", C.c_int32), ("norm_var", C.c_int32),
+                ("fsmn_input_affine_dim", C.c_int32), ("fsmn_linear_dim", C.c_int32), ("fsmn_proj_dim", C.c_int32),
+                ("fsmn_left_order", C.c_int32), ("fsmn_right_order", C.c_int32),
+                ("fsmn_output_affine_dim", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/wekws_b200.h declares
@@ -59,6 +63,9 @@ SIGNATURES = {
                                       C.c_int64, C.c_int64, C.c_uint32, C.c_void_p]),
     "wekws_det_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wekws_context_expand_frames": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "wekws_context_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_int64, C.c_void_p]),
     "wekws_pipeline_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint32, C.c_void_p]),

@@ -18,6 +18,11 @@ _BASE = {
                 backbone=dict(type="tcn", ds=False, num_layers=4, kernel_size=8, dropout=0.1)),
     # examples/hi_xiaowen/s0/conf/gru.yaml:26-32
     "gru": dict(hidden_dim=128, preprocessing=dict(type="linear"), backbone=dict(type="gru", num_layers=2)),
+    # examples/hi_xiaowen/s0/conf/fsmn_ctc.yaml:36-55 (input_dim 400 = 80-dim fbank x context 2+1+2, output_dim 2599)
+    "fsmn": dict(hidden_dim=128, preprocessing=dict(type="none"),
+                 backbone=dict(type="fsmn", input_affine_dim=140, num_layers=4, linear_dim=250, proj_dim=128,
+                               left_order=10, right_order=2, left_stride=1, right_stride=1, output_affine_dim=140),
+                 classifier=dict(type="identity", dropout=0.1), activation=dict(type="identity")),
 }
 
 

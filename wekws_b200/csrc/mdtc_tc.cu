@@ -1,28 +1,31 @@
-// Tensor-core (tcgen05 / TMEM) fused MDTC forward for hidden_dim 64 -- the throughput path.
+// Tensor-core (tcgen05 / TMEM) fused MDTC forward for hidden_dim 64 -- the throughput path (round-2 layout).
 //
 // Same math as conv_backbone.cu (KWSModel.forward, reference wekws/model/kws_model.py:65-76 with
 // mdtc.py:95-121 blocks, BatchNorm folded), but every dense GEMM (first Linear 80->64 and the 34
 // pointwise 64x64 convolutions) runs on the 5th-gen tensor cores:
-//   * bf16 "x3" operand split (tc_common.cuh): result within ~2^-17 of fp32 (posterior error ~5e-6, bar 1e-4);
-//   * the A operand (activations) lives in TENSOR MEMORY: compute threads write their row with tcgen05.st,
-//     the MMA reads it from TMEM (tcgen05.mma, A-from-TMEM form); B (weights) is a pre-swizzled K-major
-//     SWIZZLE_128B image in shared memory, streamed by cp.async.bulk into a 2-slot ring;
+//   * bf16 "x3" operand split (tc_common.cuh): result within ~2^-16 of fp32 (posterior error ~1e-5, bar 1e-4);
+//   * the A operand (activations) lives in TENSOR MEMORY: a thread writes its row with tcgen05.st, the MMA reads
+//     it from TMEM (tcgen05.mma, A-from-TMEM form); B (weights) is a pre-swizzled K-major SWIZZLE_128B image in
+//     shared memory, streamed by cp.async.bulk into a 2-slot ring;
 //   * accumulators in TMEM, read back with tcgen05.ld.  Per tile: 64 columns D + 48 hi + 48 lo.
 //
-// One CTA per SM holds ALL of its streams (up to 7 x 40 frames) resident for the whole network: the
-// residual stream X[c][col] (fp32, time-minor, every stream's cache slice directly in front of its
-// frames so a dilated tap is a column offset) never leaves shared memory, and up to THREE 128-row
-// tiles are in flight.  19 warps: 16 compute, 1 MMA issuer (+ weight / vector ring), 2 loaders (cache
-// slices by 2-D TMA tensor copies, scattered into X).  No CTA-wide barrier in the steady state:
+// One CTA per SM holds ALL of its streams (up to 7 x 40 frames) resident for the whole network.  What changed
+// against round 1 (2025 warp-instructions per frame, every warp in the same phase at the same time):
+//   * the residual stream is CHANNEL-MINOR: X[col][64 ch] (256 B per frame column, every stream's cache slice in the
+//     columns directly in front of its frames, so a dilated tap is a column offset), 16-byte chunks XOR-swizzled
+//     by (col & 7) -- a thread reads 8 channels of a tap with two conflict-free LDS.128 instead of 8 LDS.32;
+//   * a thread owns a whole ROW (all 64 channels of one frame): 4 warps = one 128-row tile = one GROUP, and the
+//     three groups run the network independently of each other (own mbarriers, a 128-thread named barrier per
+//     block, own MMA-issue warp), so the CUDA-core phases of one tile overlap the tensor-core phases of the others
+//     without any CTA-wide lock step;
+//   * depthwise taps and bias adds use packed fma.rn.f32x2 / add.rn.f32x2; the ReLU of the pointwise-1 epilogue is
+//     folded into the bf16 split (cvt.rz.relu / cvt.rn.relu), the split itself is 5 instructions per pair;
+//   * each group stores its new cache slices while its own pointwise-1 GEMM runs.
 //
-//   compute : DW(0) DW(1) DW(2) EPI1(0) EPI1(1) EPI1(2) EPI2(0) EPI2(1) EPI2(2) |bar|     (per block)
-//   issuer  :      MMA1(0) MMA1(1) MMA1(2)   MMA2(0)  MMA2(1)  MMA2(2)   + next block's weights
-//   loaders :      slices(blk+1) of every tile as soon as its DW is done
-//
-// A lane owns one ROW (frame) of a tile everywhere: row = 32 * (warp % 4) + lane is also its TMEM lane.
+// 15 warps: 12 compute (group g = warp / 4, TMEM lane quarter q = warp % 4; lane 0 of a group's first warp issues the
+// group's MMAs once the other three warps have arrived), 1 weight / vector ring warp, 2 loaders (cache slices by 2-D
+// TMA tensor copies into landing slots, transposed into X).
 #include <stdlib.h>
-
-#include <type_traits>
 
 #include "common.cuh"
 #include "mdtc_tc.h"
@@ -34,32 +37,42 @@ namespace {
 
 using namespace tc;
 
-constexpr int NCW = 16;                    // compute warps
-constexpr int NCT = NCW * 32;              // compute threads
-constexpr int NT_TC = NCT + 96;            // + MMA-issue warp (NCW) + two loader warps (NCW+1, NCW+2)
+constexpr int NG = 3;                      // row tiles in flight == compute groups
+constexpr int NCW = 4 * NG;                // compute warps
+constexpr int W_WGT = NCW;                 // warp 12: weight / vector ring
+constexpr int W_LD = W_WGT + 1;            // warps 13, 14: cache loaders
+constexpr int NT_TC = (W_LD + 2) * 32;     // 480 threads: <= 4 warps per scheduler -> 128 registers per thread
 constexpr int C = 64;
-constexpr int NTILE = 3;                   // row tiles in flight
-constexpr int RPX = 512;                   // row stride (floats) of X[c][.]
-constexpr int XCOLS = 504;                 // usable columns (n_streams * Lw <= XCOLS); column XCOLS absorbs padding rows
-constexpr int X_BYTES = 64 * RPX * 4;      // 131072
+constexpr int XCOLS = 504;                 // frame columns of X (n_streams * Lw <= XCOLS)
+constexpr int X_BYTES = XCOLS * 256;       // 129024: X[col][64] fp32
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
-constexpr int NSLOT = 7;                   // loader 0: slots 0..3, loader 1: slots 4..6 (depth 3 / 2 slices in flight)
+constexpr int NSLOT = 7;                   // loader 0: slots 0..3, loader 1: slots 4..6
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
 constexpr int VEC_FLOATS = 512;            // per-block vectors: (K + 3) * 64 floats, K <= 5
 constexpr int OFF_X = 0;
-constexpr int OFF_STG = OFF_X + X_BYTES;                   // 131072
-constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 188416
-constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 221184
-constexpr int SMEM_TOTAL = OFF_VEC + 2 * VEC_FLOATS * 4 + 1024;   // 226304 incl. alignment slack
+constexpr int OFF_STG = OFF_X + X_BYTES;                   // 129024
+constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 186368 (1024-aligned: SWIZZLE_128B images)
+constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 219136
+constexpr int SMEM_TOTAL = OFF_VEC + 2 * VEC_FLOATS * 4 + 1024;   // 224256 incl. alignment slack
+static_assert(OFF_W % 1024 == 0, "weight images must be 1024-byte aligned");
 static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
-// TMEM columns of tile i: [160 i, 160 i + 64) accumulator, + 64.. A hi (<= 48 cols), + 112.. A lo
+// TMEM columns of tile i: [160 i, 160 i + 64) accumulator, + 64.. A hi (<= 48 cols = K 96), + 112.. A lo
 constexpr int TM_TILE = 160, TM_AHI = 64, TM_ALO = 112, TM_COLS = 512;
 
-__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+__device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// byte offset of channel ch of frame column col inside X: the 16-byte chunk holding channels 8m..8m+3 sits at chunk
+// (m ^ (col & 7)) of the first 128 bytes, channels 8m+4..8m+7 at the same chunk of the second 128 bytes
+__device__ __forceinline__ uint32_t xoff(int col, int ch) {
+  const uint32_t c = (uint32_t)ch, k = (uint32_t)col;
+  return (k << 8) + ((c & 4u) << 5) + ((((c >> 3) ^ k) & 7u) << 4) + ((c & 3u) << 2);
 }
 // 2-D TMA tensor copy global -> shared (box given by the tensor map), completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
@@ -67,56 +80,48 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
                ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
-// splits 8 consecutive K values of this thread's row into 4 hi + 4 lo packed columns and stores them to TMEM
-__device__ __forceinline__ void split_to_tmem(const float (&v)[8], uint32_t t_hi, uint32_t t_lo) {
-  uint32_t h[4], l[4];
-  split2(v[0], v[1], h[0], l[0]); split2(v[2], v[3], h[1], l[1]);
-  split2(v[4], v[5], h[2], l[2]); split2(v[6], v[7], h[3], l[3]);
-  tmem_st4(t_hi, h);
-  tmem_st4(t_lo, l);
-}
 
+// KT: compile-time tap count (5 = every shipped mdtc config; 0 = read a.ktaps, taps guarded one by one)
+template <int KT>
 __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  __shared__ uint64_t mma_bar[NTILE], halo_bar[NTILE], a_rdy[NTILE], h_free[NTILE];
+  __shared__ uint64_t mma_bar[NG], halo_bar[NG], a_rdy[NG], h_free[NG];
   __shared__ uint64_t w_bar[2], w_free[2], vec_bar[2], stg_bar[NSLOT];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_issuer = warp == NCW, is_loader = warp > NCW;
-  const int q = warp & 3, g = (warp >> 2) & 3;    // TMEM lane quarter / 16-column group of this (compute) warp
-  const int row = 32 * q + lane;                  // the row of every tile this thread owns
-  const int T = a.T, K = a.ktaps;
+  const int T = a.T, K = KT ? KT : a.ktaps;
   const float* vec = a.vec;
 
-  float* X = reinterpret_cast<float*>(base + OFF_X);
   float* STG = reinterpret_cast<float*>(base + OFF_STG);
   uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
   float* VEC = reinterpret_cast<float*>(base + OFF_VEC);
   uint32_t sbase;                                  // shared-window address of `base`, pinned in a register
   asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(base)));
+  const uint32_t xs = sbase + OFF_X;
 
   if (tid == 0) {
-    for (int i = 0; i < NTILE; ++i) {
-      mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 2); mbar_init(&a_rdy[i], NCW); mbar_init(&h_free[i], NCW);
+    for (int i = 0; i < NG; ++i) {
+      mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 2); mbar_init(&a_rdy[i], 3); mbar_init(&h_free[i], 4);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&w_bar[i], 1); mbar_init(&w_free[i], 1); mbar_init(&vec_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&w_bar[i], 1); mbar_init(&w_free[i], NG); mbar_init(&vec_bar[i], 1); }
     for (int i = 0; i < NSLOT; ++i) mbar_init(&stg_bar[i], 1);
     mbar_fence_init();
   }
-  if (is_issuer) tmem_alloc(&tmem_slot, TM_COLS);
+  if (warp == W_WGT) tmem_alloc(&tmem_slot, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  // phase parities (every waiter keeps its own copy; all copies advance in lock step)
-  uint32_t mma_par = 0, halo_par = 0, ar_par = 0, hf_par = 0;       // bit i = parity of tile i's barrier
-  uint32_t w_par[2] = {0, 0}, wf_par[2] = {0, 0}, vec_par[2] = {0, 0};
+  // phase parities: every waiter keeps its own copy; all copies of a barrier advance in lock step
+  uint32_t mma_par = 0, halo_par = 0, ar_par = 0, vec_par = 0;       // compute / issuer
+  uint32_t hf_par = 0;                                               // loaders: bit i = tile i
+  uint32_t w_par = 0, wf_par = 0;                                    // bit s = slot s
   uint32_t jobctr = 0;                                               // loader: landing-slot use counter
   const uint32_t idesc = make_idesc_bf16(128, 64);
   const int natoms = (a.idim + 63) / 64;
-  const int PADR = a.padr, Lw = a.padr + ((T + 3) & ~3);
+  const int PADR = a.padr, Lw = a.padr + T;
   const int spt = a.spt;                                             // streams per tile
 
   // balanced contiguous partition of the streams over the grid
@@ -133,8 +138,294 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
     const int ntile = (ns + spt - 1) / spt;
     auto tile_streams = [&](int i) { return min(spt, ns - i * spt); };  // streams of tile i (sequential fill)
 
-    if (is_issuer) {
-      // ================================================================== MMA-ISSUE WARP (lane 0 works)
+    if (warp < NCW) {
+      // ================================================================== COMPUTE GROUPS (4 warps per tile)
+      const int grp = warp >> 2, q = warp & 3, row = 32 * q + lane;
+      if (grp < ntile) {
+        const int nst = tile_streams(grp), rows = nst * T;
+        const bool live = row < rows, q_live = 32 * q < rows;
+        const int s = live ? row / T : 0, tt = live ? row - s * T : 0;
+        const int sg = grp * spt + s;                      // stream index inside the pass
+        const int col = sg * Lw + PADR + tt;               // this row's frame column (dead rows alias a valid one)
+        const uint32_t t_own = xs + ((uint32_t)col << 8) + (((uint32_t)col & 7u) << 4);
+        const uint32_t tm_row = tmem + ((uint32_t)(32 * q) << 16) + TM_TILE * grp;
+        const uint32_t vsm = sbase + OFF_VEC;
+        float part[8];                                     // classifier partial sums of this row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[j] = 0.f;
+
+        // MMA issue (lane 0 of the group's first warp): 3-pass bf16x3 GEMM D (+)= A * W^T, A from TMEM (8 packed
+        // columns per K step), W image in shared memory
+        uint64_t dW_hi[2], dW_lo[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          dW_hi[sl] = make_sdesc_sw128(sbase + OFF_W + sl * W_SLOT);
+          dW_lo[sl] = make_sdesc_sw128(sbase + OFF_W + sl * W_SLOT + 8192);
+        }
+        const uint32_t dcol = tmem + TM_TILE * grp;
+        auto issue_gemm = [&](int a_col, int slot, int ksteps, uint32_t& acc) {
+          const uint32_t ahi = dcol + TM_AHI + a_col, alo = dcol + TM_ALO + a_col;
+          for (int k = 0; k < ksteps; ++k) { umma_bf16_ts(dcol, ahi + 8 * k, dW_hi[slot] + 2 * k, idesc, acc); acc = 1; }
+          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(dcol, alo + 8 * k, dW_hi[slot] + 2 * k, idesc, 1);
+          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(dcol, ahi + 8 * k, dW_lo[slot] + 2 * k, idesc, 1);
+        };
+        // this warp's rows of the operand are in TMEM: warps 1..3 arrive and move on; warp 0 waits for them and issues
+        // GEMM `job` (-1: first Linear over slot 0 (+1); 0 / 1: the block's pointwise-1 / conv2 GEMM over that slot)
+        auto hand_over = [&](int job) {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (q != 0) {
+            if (lane == 0) mbar_arrive(&a_rdy[grp]);
+            return;
+          }
+          mbar_wait(&a_rdy[grp], ar_par);
+          ar_par ^= 1;
+          tc_fence_after();
+          if (lane == 0) {
+            if (job < 0) {
+              mbar_wait(&w_bar[0], w_par & 1);
+              if (natoms > 1) mbar_wait(&w_bar[1], (w_par >> 1) & 1);
+              uint32_t acc = 0;
+              issue_gemm(0, 0, (min(a.idim, 64) + 15) >> 4, acc);
+              if (natoms > 1) issue_gemm(32, 1, (a.idim - 64 + 15) >> 4, acc);
+              umma_commit(&mma_bar[grp]);
+              umma_commit(&w_free[0]);
+              if (natoms > 1) umma_commit(&w_free[1]);
+            } else {
+              mbar_wait(&w_bar[job], (w_par >> job) & 1);
+              uint32_t acc = 0;
+              issue_gemm(0, job, 4, acc);
+              umma_commit(&mma_bar[grp]);
+              umma_commit(&w_free[job]);      // the slot may be refilled once these MMAs are done
+            }
+          }
+          w_par ^= job < 0 ? (natoms > 1 ? 3u : 1u) : (1u << job);
+          __syncwarp();
+        };
+        auto wait_mma = [&]() {
+          mbar_wait(&mma_bar[grp], mma_par);
+          mma_par ^= 1;
+          tc_fence_after();
+        };
+
+        // ---- features (+CMVN) -> bf16x3 operand rows in TMEM (8 K values = 4 packed columns per chunk)
+        if (q_live) {
+          const int nch = ((a.idim + 15) >> 4) * 2;        // 16-byte chunks incl. zero padding to a K step
+          const float* src0 = a.feats + (size_t)(b0 + sg) * a.feat_bstride + (size_t)tt * a.idim;
+          for (int ch = 0; ch < nch; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = 0.f;
+            const int k0 = ch * 8;
+            if (live && k0 < a.idim) {
+              const float4 f0 = __ldg(reinterpret_cast<const float4*>(src0 + k0));
+              const float4 f1 = __ldg(reinterpret_cast<const float4*>(src0 + k0) + 1);
+              v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+              if (a.has_cmvn) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (v[u] - __ldg(vec + a.v_mean + k0 + u)) * __ldg(vec + a.v_istd + k0 + u);
+              }
+            }
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) split_pair_rn(pack2(v[2 * u], v[2 * u + 1]), h[u], l[u]);
+            tmem_st4(tm_row + TM_AHI + 4 * ch, h);
+            tmem_st4(tm_row + TM_ALO + 4 * ch, l);
+          }
+        }
+        hand_over(-1);
+        // ---- x = relu(D + bp) -> X                                            (subsampling.py:53-57)
+        wait_mma();
+        if (q_live) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t d[32];
+            tmem_ld32_nowait(tm_row + 32 * half, d);
+            tmem_ld_wait();
+            const float4* bp = reinterpret_cast<const float4*>(vec + a.v_bp + 32 * half);
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+              const float4 ba = __ldg(bp + 2 * mm), bb = __ldg(bp + 2 * mm + 1);
+              auto E = [&](int u) { return __uint_as_float(d[8 * mm + u]); };
+              const f32x2 o0 = pack2(fmaxf(E(0) + ba.x, 0.f), fmaxf(E(1) + ba.y, 0.f));
+              const f32x2 o1 = pack2(fmaxf(E(2) + ba.z, 0.f), fmaxf(E(3) + ba.w, 0.f));
+              const f32x2 o2 = pack2(fmaxf(E(4) + bb.x, 0.f), fmaxf(E(5) + bb.y, 0.f));
+              const f32x2 o3 = pack2(fmaxf(E(6) + bb.z, 0.f), fmaxf(E(7) + bb.w, 0.f));
+              const uint32_t ax = t_own ^ ((uint32_t)(4 * half + mm) << 4);
+              if (live) { sts_2x2(ax, o0, o1); sts_2x2(ax + 128, o2, o3); }
+            }
+          }
+        }
+        tc_fence_before();
+        group_barrier(grp);                  // X of the tile complete before the first depthwise conv reads across rows
+
+        // ---- blocks
+        for (int blk = 0; blk < a.nblocks; ++blk) {
+          const int d = a.dil[blk], pad = d * (K - 1);
+          const uint32_t vb = vsm + (uint32_t)(blk & 1) * (VEC_FLOATS * 4);
+          const bool stack_end = (blk > 0) && (blk % a.stack_size == 0);
+          // ---------------- depthwise dilated conv (+folded BN) -> operand rows in TMEM      (mdtc.py:56-57)
+          mbar_wait(&vec_bar[blk & 1], (vec_par >> (blk & 1)) & 1);
+          vec_par ^= 1u << (blk & 1);
+          mbar_wait(&halo_bar[grp], halo_par);
+          halo_par ^= 1;
+          if (q_live) {
+            uint32_t tj[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const uint32_t cj = (uint32_t)(col - pad + j * d);
+              tj[j] = xs + (cj << 8) + ((cj & 7u) << 4);
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              f32x2 acc0, acc1, acc2, acc3;
+              lds_2x2(vb + (uint32_t)(K * C + 8 * m) * 4, acc0, acc1);
+              lds_2x2(vb + (uint32_t)(K * C + 8 * m) * 4 + 16, acc2, acc3);
+#pragma unroll
+              for (int j = 0; j < 5; ++j) {
+                if (KT ? j < KT : j < K) {
+                  const uint32_t aj = tj[j] ^ ((uint32_t)m << 4);
+                  f32x2 x0, x1, x2, x3, w0, w1, w2, w3;
+                  lds_2x2(aj, x0, x1);
+                  lds_2x2(aj + 128, x2, x3);
+                  lds_2x2(vb + (uint32_t)(j * C + 8 * m) * 4, w0, w1);
+                  lds_2x2(vb + (uint32_t)(j * C + 8 * m) * 4 + 16, w2, w3);
+                  acc0 = fma2(w0, x0, acc0);
+                  acc1 = fma2(w1, x1, acc1);
+                  acc2 = fma2(w2, x2, acc2);
+                  acc3 = fma2(w3, x3, acc3);
+                }
+              }
+              uint32_t h[4], l[4];
+              split_pair_rn(acc0, h[0], l[0]);
+              split_pair_rn(acc1, h[1], l[1]);
+              split_pair_rn(acc2, h[2], l[2]);
+              split_pair_rn(acc3, h[3], l[3]);
+              tmem_st4(tm_row + TM_AHI + 4 * m, h);
+              tmem_st4(tm_row + TM_ALO + 4 * m, l);
+            }
+          }
+          hand_over(0);
+          // ---------------- new cache slices of this tile while its pointwise-1 GEMM runs:
+          // out_cache[b][c][off + j] = cat[c][T + j] (mdtc.py:113).  A warp reads 8 columns x 4 channels per request
+          // (conflict-free in the swizzled layout); 8 lanes write 32 contiguous bytes of one cache row.
+          {
+            const int off = a.coff[blk];
+            const int npj = pad >= 8 ? pad >> 3 : 1, lgn = 31 - __clz(npj), nitem = nst * 16 * npj;
+            const int jlow = lane & 7, chi = lane >> 3;
+            for (int it = q; it < nitem; it += 4) {
+              const int jh = it & (npj - 1), r = it >> lgn, cq4 = r & 15, s2 = r >> 4;
+              const int c = 4 * cq4 + chi, jj = 8 * jh + jlow;
+              if (jj < pad) {
+                const int sg2 = grp * spt + s2;
+                const float v = lds_f32(xs + xoff(sg2 * Lw + PADR + T - pad + jj, c));
+                a.out_cache[((size_t)(b0 + sg2) * C + c) * a.P + off + jj] = v;
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_free[grp]);      // the tile's cache columns may be overwritten
+          }
+          // ---------------- h = relu(D + b1) -> operand rows in TMEM                          (mdtc.py:115)
+          wait_mma();
+          if (q_live) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t dd[32];
+              tmem_ld32_nowait(tm_row + 32 * half, dd);
+              tmem_ld_wait();
+              uint32_t h[16], l[16];
+#pragma unroll
+              for (int mm = 0; mm < 4; ++mm) {
+                f32x2 b0v, b1v, b2v, b3v;
+                lds_2x2(vb + (uint32_t)((K + 1) * C + 32 * half + 8 * mm) * 4, b0v, b1v);
+                lds_2x2(vb + (uint32_t)((K + 1) * C + 32 * half + 8 * mm) * 4 + 16, b2v, b3v);
+                auto E = [&](int u) { return __uint_as_float(dd[8 * mm + u]); };
+                split_pair_rz_relu(add2(pack2(E(0), E(1)), b0v), h[4 * mm + 0], l[4 * mm + 0]);
+                split_pair_rz_relu(add2(pack2(E(2), E(3)), b1v), h[4 * mm + 1], l[4 * mm + 1]);
+                split_pair_rz_relu(add2(pack2(E(4), E(5)), b2v), h[4 * mm + 2], l[4 * mm + 2]);
+                split_pair_rz_relu(add2(pack2(E(6), E(7)), b3v), h[4 * mm + 3], l[4 * mm + 3]);
+              }
+              tmem_st16(tm_row + TM_AHI + 16 * half, h);
+              tmem_st16(tm_row + TM_ALO + 16 * half, l);
+            }
+          }
+          hand_over(1);
+          // ---------------- x' = relu(D + b2 + x) -> X; classifier partial sums at the end of a stack
+          wait_mma();                                                          // (mdtc.py:116-118, 266-273)
+          if (q_live) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t dd[32];
+              tmem_ld32_nowait(tm_row + 32 * half, dd);
+              tmem_ld_wait();
+#pragma unroll
+              for (int mm = 0; mm < 4; ++mm) {
+                const int m = 4 * half + mm;
+                const uint32_t ax = t_own ^ ((uint32_t)m << 4);
+                f32x2 b0v, b1v, b2v, b3v, r0, r1, r2, r3;
+                lds_2x2(vb + (uint32_t)((K + 2) * C + 8 * m) * 4, b0v, b1v);
+                lds_2x2(vb + (uint32_t)((K + 2) * C + 8 * m) * 4 + 16, b2v, b3v);
+                lds_2x2(ax, r0, r1);
+                lds_2x2(ax + 128, r2, r3);
+                auto E = [&](int u) { return __uint_as_float(dd[8 * mm + u]); };
+                float o[8];
+                unpack2(add2(add2(pack2(E(0), E(1)), b0v), r0), o[0], o[1]);
+                unpack2(add2(add2(pack2(E(2), E(3)), b1v), r1), o[2], o[3]);
+                unpack2(add2(add2(pack2(E(4), E(5)), b2v), r2), o[4], o[5]);
+                unpack2(add2(add2(pack2(E(6), E(7)), b3v), r3), o[6], o[7]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.f);
+                if (live) {
+                  sts_2x2(ax, pack2(o[0], o[1]), pack2(o[2], o[3]));
+                  sts_2x2(ax + 128, pack2(o[4], o[5]), pack2(o[6], o[7]));
+                }
+                if (stack_end) {      // the classifier is linear: W_c (sum of stack outputs) = sum of W_c (stack output)
+                  const float* wc = vec + a.v_wc + (8 * m) * a.odim;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    if (j < a.odim) {
+                      float p = part[j];
+#pragma unroll
+                      for (int u = 0; u < 8; ++u) p = fmaf(__ldg(wc + u * a.odim + j), o[u], p);
+                      part[j] = p;
+                    }
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          group_barrier(grp);                // x' of every row of the tile complete before the next block's conv
+        }
+
+        // ---- classifier bias + activation: the row's sums are complete in registers
+        if (live) {
+          float* o = a.out + (size_t)(b0 + sg) * a.out_bstride + (size_t)tt * a.odim;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < a.odim) {
+              float y = part[j] + __ldg(vec + a.v_bc + j);
+              if (a.act == WEKWS_ACT_SIGMOID) y = sigmoidf_acc(y);
+              o[j] = y;
+            }
+          }
+        }
+      } else if (q == 0 && lane == 0) {
+        // a group without streams in this pass still releases every weight slot use (w_free counts NG arrivals)
+        mbar_wait(&w_bar[0], w_par & 1);
+        mbar_arrive(&w_free[0]);
+        if (natoms > 1) { mbar_wait(&w_bar[1], (w_par >> 1) & 1); mbar_arrive(&w_free[1]); }
+        w_par ^= natoms > 1 ? 3u : 1u;
+        for (int blk = 0; blk < a.nblocks; ++blk)
+          for (int job = 0; job < 2; ++job) {
+            mbar_wait(&w_bar[job], (w_par >> job) & 1);
+            w_par ^= 1u << job;
+            mbar_arrive(&w_free[job]);
+          }
+      }
+    } else if (warp == W_WGT) {
+      // ================================================================== WEIGHT / VECTOR RING (lane 0 works)
       if (lane == 0) {
         auto load_w = [&](int slot, const uint8_t* src) {
           mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
@@ -145,75 +436,35 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, vec + a.v_blocks + blk * a.v_blk_stride, (uint32_t)(a.v_blk_stride * 4),
                    &vec_bar[blk & 1]);
         };
-        // 3-pass bf16x3 GEMM of tile i: D (+)= A * W^T; A from TMEM (8 columns per K step), W image in smem
-        auto issue_gemm = [&](int i, int a_col, uint64_t dw_hi, uint64_t dw_lo, int ksteps, uint32_t& acc) {
-          const uint32_t d = tmem + TM_TILE * i, ahi = d + TM_AHI + a_col, alo = d + TM_ALO + a_col;
-          for (int k = 0; k < ksteps; ++k) { umma_bf16_ts(d, ahi + 8 * k, dw_hi + 2 * k, idesc, acc); acc = 1; }
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, alo + 8 * k, dw_hi + 2 * k, idesc, 1);
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dw_lo + 2 * k, idesc, 1);
+        auto wait_free = [&](int slot) {             // every tile's MMAs on the slot's current weights are done
+          mbar_wait_backoff(&w_free[slot], (wf_par >> slot) & 1);
+          wf_par ^= 1u << slot;
         };
-        auto wait_a = [&](int i) {                   // operand rows of tile i complete
-          mbar_wait(&a_rdy[i], (ar_par >> i) & 1);
-          ar_par ^= 1u << i;
-          tc_fence_after();
-        };
-        uint64_t dW_hi[2], dW_lo[2];
-        for (int i = 0; i < 2; ++i) {
-          dW_hi[i] = make_sdesc_sw128(smem_u32(Wslot[i])); dW_lo[i] = make_sdesc_sw128(smem_u32(Wslot[i]) + 8192);
-        }
-        const int ks0 = (min(a.idim, 64) + 15) >> 4, ks1 = natoms > 1 ? (a.idim - 64 + 15) >> 4 : 0;
-
-        // ---- first Linear
         load_vec(0);
+        if (a.nblocks > 1) load_vec(1);
         load_w(0, a.wimg);
         if (natoms > 1) load_w(1, a.wimg + W_SLOT);
-        mbar_wait(&w_bar[0], w_par[0]); w_par[0] ^= 1;
-        if (natoms > 1) { mbar_wait(&w_bar[1], w_par[1]); w_par[1] ^= 1; }
-        for (int i = 0; i < ntile; ++i) {
-          wait_a(i);
-          uint32_t acc = 0;
-          issue_gemm(i, 0, dW_hi[0], dW_lo[0], ks0, acc);
-          if (natoms > 1) issue_gemm(i, 32, dW_hi[1], dW_lo[1], ks1, acc);
-          umma_commit(&mma_bar[i]);
-        }
-        umma_commit(&w_free[0]);
-        mbar_wait(&w_free[0], wf_par[0]); wf_par[0] ^= 1;   // both weight slots are busy until these GEMMs finish
-        load_w(0, a.wimg + 2 * W_SLOT);
-        load_w(1, a.wimg + 3 * W_SLOT);
-
-        // ---- blocks
-        for (int blk = 0; blk < a.nblocks; ++blk) {
-          const bool more = blk + 1 < a.nblocks;
-          const uint8_t* wnext = a.wimg + (size_t)(2 + 2 * (blk + 1)) * W_SLOT;
-          for (int phase = 0; phase < 2; ++phase) {        // phase 0: pointwise-1 GEMMs, phase 1: conv2 GEMMs
-            mbar_wait(&w_bar[phase], w_par[phase]); w_par[phase] ^= 1;
-            for (int i = 0; i < ntile; ++i) {
-              wait_a(i);
-              uint32_t acc = 0;
-              if (a.debug & 1) { mbar_arrive(&mma_bar[i]); }
-              else { issue_gemm(i, 0, dW_hi[phase], dW_lo[phase], 4, acc); umma_commit(&mma_bar[i]); }
-            }
-            umma_commit(&w_free[phase]);
-            if (phase == 1) {      // slot 0 drained long ago: refill it while the conv2 GEMMs run
-              mbar_wait(&w_free[0], wf_par[0]); wf_par[0] ^= 1;
-              if (more) load_w(0, wnext);
-            }
-          }
-          mbar_wait(&w_free[1], wf_par[1]); wf_par[1] ^= 1;
-          if (more) load_w(1, wnext + W_SLOT);
-          // VEC[(blk+1)&1] was last read by block blk-1, which every compute warp has left
-          if (more) load_vec(blk + 1);
+        // slot 0 carries: Linear atom 0, W1(0), W1(1), ...; slot 1: [Linear atom 1], W2(0), W2(1), ...
+        for (int b = 0; b <= a.nblocks; ++b) {
+          const uint8_t* wb = a.wimg + (size_t)(2 + 2 * b) * W_SLOT;
+          wait_free(0);
+          if (b < a.nblocks) load_w(0, wb);
+          // every tile has handed over DW(b-1), hence finished block b-2: VEC[b & 1] is free
+          if (b >= 2 && b < a.nblocks) load_vec(b);
+          if (b > 0 || natoms > 1) wait_free(1);
+          if (b < a.nblocks) load_w(1, wb + W_SLOT);
         }
       }
-    } else if (is_loader) {
+    } else {
       // ================================================================== LOADER WARPS
       // loader l owns the streams sg with sg % 2 == l.  Per (block, stream): one 2-D TMA copy [64][pad] into a
-      // landing slot, then the warp scatters it into the pad columns in front of the stream's frames in X.
-      const int l = warp - NCW - 1;
+      // landing slot, then the warp transposes it into the pad columns in front of the stream's frames in X.
+      const int l = warp - W_LD;
       const int nmine = (ns - l + 1) / 2;              // my streams: l, l + 2, ...
       const int njobs = a.nblocks * nmine;
-      const bool have_cache = a.in_cache != nullptr && !(a.debug & 16);
+      const bool have_cache = a.in_cache != nullptr;
       const int nsl = l == 0 ? 4 : 3, slot0 = l == 0 ? 0 : 4;   // my landing slots: a ring of nsl
+      const int jlow = lane & 7, chi = lane >> 3;
       auto issue_tma = [&](int k) {                    // lane 0; job k = (blk, my m-th stream)
         const int blk = k / nmine, sg = l + 2 * (k - blk * nmine);
         const int pad = a.dil[blk] * (K - 1);
@@ -226,8 +477,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       int k = 0;
       for (int blk = 0; blk < a.nblocks; ++blk) {
         const int pad = a.dil[blk] * (K - 1);
+        const int npj = pad >= 8 ? pad >> 3 : 1, lg = 31 - __clz(npj);
+        const int fx = (pad == 32 ? chi : pad == 16 ? (chi >> 1) : 0) & (npj - 1);   // read-bank spreading
         for (int i = 0; i < ntile; ++i) {
-          // X's pad columns of tile i are free once DW(i, blk-1) is done (at blk 0 they are free from the start)
+          // X's pad columns of tile i are free once DW + cache stores (i, blk-1) are done (at blk 0: from the start)
           if (blk > 0) {
             if (lane == 0) mbar_wait_backoff(&h_free[i], (hf_par >> i) & 1);
             hf_par ^= 1u << i;
@@ -236,21 +489,21 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           for (int sg = i * spt; sg < i * spt + tile_streams(i); ++sg) {
             if ((sg & 1) != l) continue;
             if (have_cache && lane == 0 && k + nsl - 1 < njobs) issue_tma(k + nsl - 1);   // reuses the slot of job k-1: drained
-            const int v4 = pad >> 2, sh = 31 - __clz(v4), cstep = 32 >> sh, c0 = lane >> sh, v = lane & (v4 - 1), iters = 2 * v4;
-            float* dst = X + sg * Lw + PADR - pad + c0 * RPX + 4 * v;
-            const int dstep = cstep * RPX;
+            const int colb = sg * Lw + PADR - pad;       // first cache column of this stream for this block
             if (have_cache) {
               const uint32_t use = jobctr + (uint32_t)k, slot = slot0 + use % nsl;
               if (lane == 0) mbar_wait_backoff(&stg_bar[slot], (use / nsl) & 1);
               __syncwarp();
-              const float4* src = reinterpret_cast<const float4*>(STG + slot * STG_FLOATS) + lane;
-              for (int it = 0; it < iters; it += 2) {
-                const float4 x0 = src[32 * it], x1 = src[32 * it + 32];
-                *reinterpret_cast<float4*>(dst + it * dstep) = x0;
-                *reinterpret_cast<float4*>(dst + (it + 1) * dstep) = x1;
+              const float* src = STG + slot * STG_FLOATS;
+#pragma unroll 4
+              for (int it = 0; it < 16 * npj; ++it) {
+                const int jh = it & (npj - 1), cq4 = it >> lg;
+                const int c = 4 * cq4 + chi, jj = jlow + 8 * (jh ^ fx);
+                if (jj < pad) sts_f32(xs + xoff(colb + jj, c), src[c * pad + jj]);
               }
             } else {
-              for (int it = 0; it < iters; ++it) *reinterpret_cast<float4*>(dst + it * dstep) = make_float4(0.f, 0.f, 0.f, 0.f);
+              const f32x2 z = 0ull;
+              for (int e = lane; e < pad * 16; e += 32) sts_2x2(xs + ((uint32_t)colb << 8) + 16u * (uint32_t)e, z, z);
             }
             fence_proxy_async();                     // the slot was read through the generic proxy; TMA rewrites it
             ++k;
@@ -265,294 +518,19 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         if (lane == 0) mbar_wait_backoff(&h_free[i], (hf_par >> i) & 1);
         hf_par ^= 1u << i;
       }
-    } else {
-      // ================================================================== COMPUTE WARPS
-      // this thread's row of tile i -> (stream, frame) -> X column; padding rows use the dummy column
-      int colx[NTILE], rows_i[NTILE];
-#pragma unroll
-      for (int i = 0; i < NTILE; ++i) {
-        rows_i[i] = i < ntile ? tile_streams(i) * T : 0;
-        const int s = row / T;
-        colx[i] = row < rows_i[i] ? (i * spt + s) * Lw + PADR + (row - s * T) : XCOLS;
-      }
-      const bool q_live[NTILE] = {32 * q < rows_i[0], 32 * q < rows_i[1], 32 * q < rows_i[2]};
-      const uint32_t tm_row = tmem + ((uint32_t)(32 * q) << 16);
-      const uint32_t xs = sbase + OFF_X;
-      // Cache stores go to the warps with the least depthwise work: lane quarters that are padding in some tile
-      // (e.g. tiles of 120/120/40 rows: quarters 2,3 skip tile 2).  If every quarter is equally busy, all store.
-      int nlive[4], maxlive = 0, minlive = NTILE;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        nlive[qq] = (32 * qq < rows_i[0]) + (32 * qq < rows_i[1]) + (32 * qq < rows_i[2]);
-        maxlive = max(maxlive, nlive[qq]);
-        minlive = min(minlive, nlive[qq]);
-      }
-      int nhq = 0, myrank = -1;                        // helper quarters and this warp's rank among them
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const bool helper = (maxlive == minlive) || (nlive[qq] == minlive);
-        if (helper) { if (qq == q) myrank = nhq; ++nhq; }
-      }
-      const int n_store_thr = nhq * 4 * 32;            // 4 warps (g = 0..3) per quarter
-      const int store_idx = myrank < 0 ? -1 : (g * nhq + myrank) * 32 + lane;
-      float part[NTILE][8];                          // classifier partial sums over this thread's 16 channels
-#pragma unroll
-      for (int i = 0; i < NTILE; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) part[i][j] = 0.f;
-
-      auto hand_over = [&](auto tc) {                // this warp's rows of tile i are in TMEM
-        constexpr int i = decltype(tc)::value;
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_rdy[i]);
-      };
-      auto wait_mma = [&](auto tc) {
-        constexpr int i = decltype(tc)::value;
-        mbar_wait(&mma_bar[i], (mma_par >> i) & 1);
-        mma_par ^= 1u << i;
-        tc_fence_after();
-      };
-      // features of tile i (+CMVN) -> bf16x3 operand rows in TMEM (8 K values = 4 packed columns per chunk)
-      auto feat = [&](auto tc) {
-        constexpr int i = decltype(tc)::value;
-        if (q_live[i]) {
-          const int nch = ((a.idim + 15) >> 4) * 2;           // 16-byte chunks incl. zero padding to a K step
-          const bool valid = row < rows_i[i];
-          const int s = row / T, tt = row - s * T;
-          const float* src0 = a.feats + (size_t)(b0 + i * spt + s) * a.feat_bstride + (size_t)tt * a.idim;
-          for (int ch = g; ch < nch; ch += 4) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = 0.f;
-            const int k0 = ch * 8;
-            if (valid && k0 < a.idim) {
-              const float4 f0 = __ldg(reinterpret_cast<const float4*>(src0 + k0));
-              const float4 f1 = __ldg(reinterpret_cast<const float4*>(src0 + k0) + 1);
-              v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
-              if (a.has_cmvn) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (v[u] - __ldg(vec + a.v_mean + k0 + u)) * __ldg(vec + a.v_istd + k0 + u);
-              }
-            }
-            split_to_tmem(v, tm_row + TM_TILE * i + TM_AHI + 4 * ch, tm_row + TM_TILE * i + TM_ALO + 4 * ch);
-          }
-        }
-        hand_over(tc);
-      };
-      // x = relu(D + bp) -> X                                            (subsampling.py:53-57)
-      auto epi0 = [&](auto tc) {
-        constexpr int i = decltype(tc)::value;
-        wait_mma(tc);
-        if (!q_live[i]) return;
-        float d[16];
-        tmem_ld16(tm_row + TM_TILE * i + 16 * g, d);
-        float* xp = X + (16 * g) * RPX + colx[i];
-        const float4* bp = reinterpret_cast<const float4*>(vec + a.v_bp + 16 * g);
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 b = __ldg(bp + i4);
-          xp[(4 * i4 + 0) * RPX] = fmaxf(d[4 * i4 + 0] + b.x, 0.f);
-          xp[(4 * i4 + 1) * RPX] = fmaxf(d[4 * i4 + 1] + b.y, 0.f);
-          xp[(4 * i4 + 2) * RPX] = fmaxf(d[4 * i4 + 2] + b.z, 0.f);
-          xp[(4 * i4 + 3) * RPX] = fmaxf(d[4 * i4 + 3] + b.w, 0.f);
-        }
-      };
-      // new cache slice + depthwise dilated conv (+folded BN) of block blk -> operand rows of tile i in TMEM
-      auto dw = [&](auto tc, int blk) {
-        constexpr int i = decltype(tc)::value;
-        const int d = a.dil[blk], pad = d * (K - 1), off = a.coff[blk];
-        const float* vb = VEC + (blk & 1) * VEC_FLOATS;
-        if (i == 0) {                                // first use of this block's vectors
-          mbar_wait(&vec_bar[blk & 1], vec_par[blk & 1]);
-          vec_par[blk & 1] ^= 1;
-        }
-        mbar_wait(&halo_bar[i], (halo_par >> i) & 1);
-        halo_par ^= 1u << i;
-        if (q_live[i] && !(a.debug & 2)) {
-          // this warp: rows 32q.., channel groups g and g + 4; tap j of channel c reads X[c][col - pad + j*d]
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int cg = g + 4 * half;
-            const uint32_t bse = xs + 4u * (uint32_t)(cg * 8 * RPX + colx[i] - pad);
-            const float4* wv = reinterpret_cast<const float4*>(vb + cg * 8);
-            float v[8];
-            {
-              const float4 ba = wv[(K * C) / 4], bb = wv[(K * C) / 4 + 1];
-              v[0] = ba.x; v[1] = ba.y; v[2] = ba.z; v[3] = ba.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-              if (j < K) {
-                const float4 wa = wv[(j * C) / 4], wb = wv[(j * C) / 4 + 1];
-                const uint32_t aj = bse + 4u * (uint32_t)(j * d);
-                v[0] = fmaf(wa.x, lds_f32(aj + 0 * RPX * 4), v[0]);
-                v[1] = fmaf(wa.y, lds_f32(aj + 1 * RPX * 4), v[1]);
-                v[2] = fmaf(wa.z, lds_f32(aj + 2 * RPX * 4), v[2]);
-                v[3] = fmaf(wa.w, lds_f32(aj + 3 * RPX * 4), v[3]);
-                v[4] = fmaf(wb.x, lds_f32(aj + 4 * RPX * 4), v[4]);
-                v[5] = fmaf(wb.y, lds_f32(aj + 5 * RPX * 4), v[5]);
-                v[6] = fmaf(wb.z, lds_f32(aj + 6 * RPX * 4), v[6]);
-                v[7] = fmaf(wb.w, lds_f32(aj + 7 * RPX * 4), v[7]);
-              }
-            }
-            split_to_tmem(v, tm_row + TM_TILE * i + TM_AHI + 4 * cg, tm_row + TM_TILE * i + TM_ALO + 4 * cg);
-          }
-        }
-        hand_over(tc);
-      };
-      // new cache slices of every tile: out_cache[b][c][off + j] = cat[c][T + j]   (mdtc.py:113), by the helper warps;
-      // then every warp releases the tiles' cache columns to the loaders.  All of this precedes the warp's EPI1
-      // hand-overs, hence the conv2 GEMMs and EPI2 (which overwrites x) cannot start before the stores are done.
-      auto store_cache = [&](int blk) {
-        const int d = a.dil[blk], pad = d * (K - 1), off = a.coff[blk];
-        if (store_idx >= 0 && !(a.debug & 8)) {
-          for (int i = 0; i < ntile; ++i) {
-            const int nst = tile_streams(i), sg0 = i * spt;
-            if ((T & 3) == 0) {      // rows are 16-byte aligned; pad is a power of two (tc_eligible)
-              const int v4 = pad >> 2, n4 = nst * C * v4, sh = 31 - __clz(v4);
-              for (int e = store_idx; e < n4; e += n_store_thr) {
-                const int cs = e >> sh, v = e & (v4 - 1), s = cs >> 6, c = cs & 63;
-                const float4 x4 = *reinterpret_cast<const float4*>(X + c * RPX + (sg0 + s) * Lw + PADR - pad + T + 4 * v);
-                *reinterpret_cast<float4*>(a.out_cache + ((size_t)(b0 + sg0 + s) * C + c) * a.P + off + 4 * v) = x4;
-              }
-            } else {
-              const int n = nst * C * pad, sh = 31 - __clz(pad);
-              for (int e = store_idx; e < n; e += n_store_thr) {
-                const int cs = e >> sh, j = e & (pad - 1), s = cs >> 6, c = cs & 63;
-                a.out_cache[((size_t)(b0 + sg0 + s) * C + c) * a.P + off + j] = X[c * RPX + (sg0 + s) * Lw + PADR - pad + T + j];
-              }
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0)
-          for (int i = 0; i < ntile; ++i) mbar_arrive(&h_free[i]);
-      };
-      // h = relu(D + b1) -> operand rows of tile i in TMEM                  (mdtc.py:115)
-      auto epi1 = [&](auto tc, int blk) {
-        constexpr int i = decltype(tc)::value;
-        const float* b1 = VEC + (blk & 1) * VEC_FLOATS + (K + 1) * C + 16 * g;
-        wait_mma(tc);
-        if (q_live[i] && !(a.debug & 4)) {
-          float d[16];
-          tmem_ld16(tm_row + TM_TILE * i + 16 * g, d);
-#pragma unroll
-          for (int hch = 0; hch < 2; ++hch) {
-            const float4 ba = reinterpret_cast<const float4*>(b1)[2 * hch];
-            const float4 bb = reinterpret_cast<const float4*>(b1)[2 * hch + 1];
-            float v[8];
-            v[0] = fmaxf(d[hch * 8 + 0] + ba.x, 0.f); v[1] = fmaxf(d[hch * 8 + 1] + ba.y, 0.f);
-            v[2] = fmaxf(d[hch * 8 + 2] + ba.z, 0.f); v[3] = fmaxf(d[hch * 8 + 3] + ba.w, 0.f);
-            v[4] = fmaxf(d[hch * 8 + 4] + bb.x, 0.f); v[5] = fmaxf(d[hch * 8 + 5] + bb.y, 0.f);
-            v[6] = fmaxf(d[hch * 8 + 6] + bb.z, 0.f); v[7] = fmaxf(d[hch * 8 + 7] + bb.w, 0.f);
-            const int ch = 2 * g + hch;
-            split_to_tmem(v, tm_row + TM_TILE * i + TM_AHI + 4 * ch, tm_row + TM_TILE * i + TM_ALO + 4 * ch);
-          }
-        }
-        hand_over(tc);
-      };
-      // x' = relu(D + b2 + x) -> X; classifier partial sums at the end of a stack (mdtc.py:116-118, 266-273)
-      auto epi2 = [&](auto tc, int blk) {
-        constexpr int i = decltype(tc)::value;
-        const float* b2 = VEC + (blk & 1) * VEC_FLOATS + (K + 2) * C + 16 * g;
-        const bool stack_end = (blk > 0) && (blk % a.stack_size == 0);
-        wait_mma(tc);
-        if (!q_live[i] || (a.debug & 4)) return;
-        float d[16];
-        tmem_ld16(tm_row + TM_TILE * i + 16 * g, d);
-        float* xp = X + (16 * g) * RPX + colx[i];
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 b = reinterpret_cast<const float4*>(b2)[i4];
-          const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = 4 * i4 + u;
-            d[e] = fmaxf(d[e] + bb[u] + xp[e * RPX], 0.f);
-            xp[e * RPX] = d[e];
-          }
-        }
-        if (stack_end) {      // the classifier is linear: W_c (sum of stack outputs) = sum of W_c (stack output)
-          const float* wc = vec + a.v_wc + (16 * g) * a.odim;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < a.odim) {
-              float p = part[i][j];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) p = fmaf(__ldg(wc + e * a.odim + j), d[e], p);
-              part[i][j] = p;
-            }
-          }
-        }
-      };
-
-      constexpr std::integral_constant<int, 0> T0{};
-      constexpr std::integral_constant<int, 1> T1{};
-      constexpr std::integral_constant<int, 2> T2{};
-      // ---- first Linear (+ReLU)
-      feat(T0);
-      if (ntile > 1) feat(T1);
-      if (ntile > 2) feat(T2);
-      epi0(T0);
-      if (ntile > 1) epi0(T1);
-      if (ntile > 2) epi0(T2);
-      tc_fence_before();
-      compute_barrier();                     // X complete before the first depthwise conv reads across rows
-
-      // ---- blocks
-      for (int blk = 0; blk < a.nblocks; ++blk) {
-        dw(T0, blk);
-        if (ntile > 1) dw(T1, blk);
-        if (ntile > 2) dw(T2, blk);
-        store_cache(blk);
-        epi1(T0, blk);
-        if (ntile > 1) epi1(T1, blk);
-        if (ntile > 2) epi1(T2, blk);
-        epi2(T0, blk);
-        if (ntile > 1) epi2(T1, blk);
-        if (ntile > 2) epi2(T2, blk);
-        tc_fence_before();
-        compute_barrier();                   // x' of every row complete before the next block's conv
-      }
-
-      // ---- classifier + activation: reduce the 4 column-group partials of each row through X (now dead)
-      const int odim = a.odim;
-      float* scratch = X;                                             // [NTILE][4][128][odim]
-#pragma unroll
-      for (int i = 0; i < NTILE; ++i)
-        if (i < ntile) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < odim) scratch[((i * 4 + g) * 128 + row) * odim + j] = part[i][j];
-        }
-      compute_barrier();
-      for (int i = 0; i < ntile; ++i) {
-        const int nrow = tile_streams(i) * T;
-        for (int idx = tid; idx < nrow * odim; idx += NCT) {
-          const int r = idx / odim, j = idx - r * odim;
-          const int s = r / T, tt = r - s * T;
-          float y = __ldg(vec + a.v_bc + j);
-#pragma unroll
-          for (int gg = 0; gg < 4; ++gg) y += scratch[((i * 4 + gg) * 128 + r) * odim + j];
-          if (a.act == WEKWS_ACT_SIGMOID) y = sigmoidf_acc(y);
-          a.out[(size_t)(b0 + i * spt + s) * a.out_bstride + (size_t)tt * odim + j] = y;
-        }
-      }
     }
-    __syncthreads();       // pass boundary: X (and the classifier scratch inside it) is reused
+    __syncthreads();       // pass boundary: X, the landing slots and the rings are reused
   }
 
   tc_fence_before();
   __syncthreads();
-  if (is_issuer) tmem_dealloc(tmem, TM_COLS);
+  if (warp == W_WGT) tmem_dealloc(tmem, TM_COLS);
 }
 
 }  // namespace
 
 bool tc_eligible(const TcArgs& a, int padmax) {
-  if (a.idim % 8 != 0 || a.idim > 128 || a.odim > 8 || a.ktaps > 5) return false;
+  if (a.idim % 8 != 0 || a.idim > 96 || a.odim > 8 || a.ktaps > 5) return false;   // A operand: 48 TMEM columns = K 96
   if (padmax > 32 || a.P % 4 != 0) return false;
   for (int b = 0; b < a.nblocks; ++b)
   {
@@ -586,16 +564,13 @@ EncodeTiledFn encode_tiled_fn() {
 int mdtc_tc_launch(TcArgs a, int padmax, cudaStream_t st) {
   WEKWS_REQUIRE(a.T >= 1 && a.T <= 128 && a.B >= 1, "mdtc_tc_launch: bad shape");
   a.padr = (padmax + 3) & ~3;
-  const int Lw = a.padr + ((a.T + 3) & ~3);
+  const int Lw = a.padr + a.T;
   a.spt = 128 / a.T;                                   // streams per 128-row tile
   WEKWS_REQUIRE(a.spt >= 1 && Lw <= XCOLS, "mdtc_tc_launch: tile does not fit");
-  int smax = NTILE * a.spt;                            // streams resident per pass
+  int smax = NG * a.spt;                               // streams resident per pass
   if (smax > XCOLS / Lw) smax = XCOLS / Lw;
   a.smax = smax;
-  {
-    const char* dbg = getenv("WEKWS_TC_DEBUG");    // timing experiments only (results are wrong when set)
-    a.debug = dbg ? atoi(dbg) : 0;
-  }
+  a.debug = 0;
   // tensor maps over the incoming cache (B*64 rows of P floats): one per distinct slice width
   if (a.in_cache != nullptr) {
     EncodeTiledFn enc = encode_tiled_fn();
@@ -626,10 +601,12 @@ int mdtc_tc_launch(TcArgs a, int padmax, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    WEKWS_CUDA_OK(cudaFuncSetAttribute(mdtc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    WEKWS_CUDA_OK(cudaFuncSetAttribute(mdtc_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    WEKWS_CUDA_OK(cudaFuncSetAttribute(mdtc_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set[dev] = true;
   }
-  mdtc_tc_kernel<<<grid, NT_TC, SMEM_TOTAL, st>>>(a);
+  if (a.ktaps == 5) mdtc_tc_kernel<5><<<grid, NT_TC, SMEM_TOTAL, st>>>(a);
+  else mdtc_tc_kernel<0><<<grid, NT_TC, SMEM_TOTAL, st>>>(a);
   return check_launch("mdtc_tc_kernel");
 }
 

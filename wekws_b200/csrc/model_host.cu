@@ -20,6 +20,7 @@
 #include "mdtc_tc.h"
 #include "tcn_tc.h"
 #include "dstcn_tc.h"
+#include "fsmn.h"
 
 namespace wekws {
 
@@ -99,6 +100,7 @@ struct wekws_model {
   TcnTcArgs tcnargs{};
   bool ds_ok = false;                       // tensor-core path for the depthwise-separable TCN (hidden 256)
   DsTcArgs dsargs{};
+  FsmnArgs fsmn{};                          // FSMN backbone (fsmn.cu): weights live in h_vec / d_vec
 };
 
 namespace {
@@ -437,6 +439,85 @@ int pack_gru(wekws_model* m) {
   return WEKWS_OK;
 }
 
+
+// FSMN (wekws/model/fsmn.py:401-495): every matrix transposed to [K][Npad] (Npad = N rounded up to the GEMM pass width,
+// zero filled) so the kernel streams K-chunks with 16-byte cp.async; biases padded the same way; memory taps as
+// [lorder + rorder][proj] (left taps, then right taps).
+int pack_fsmn(wekws_model* m) {
+  const wekws_model_config& c = m->cfg;
+  const int idim = c.idim, A1 = c.fsmn_input_affine_dim, D = c.fsmn_linear_dim, P = c.fsmn_proj_dim;
+  const int A2 = c.fsmn_output_affine_dim, O = c.odim, L = c.num_layers, lo = c.fsmn_left_order, ro = c.fsmn_right_order;
+  WEKWS_REQUIRE(idim >= 1 && A1 >= 1 && D >= 1 && P >= 1 && A2 >= 1 && L >= 1 && L <= 16, "fsmn: bad layer dimensions");
+  WEKWS_REQUIRE(lo >= 1 && ro >= 1, "fsmn: left_order %d / right_order %d unsupported (the reference's FSMNBlock itself "
+                "breaks for right_order = 0: fsmn.py:235 slices x_pad[:, :, :-0])", lo, ro);
+  m->h_stream.clear(); m->h_vec.clear(); m->h_chunk_off.clear();
+  m->padding = lo - 1 + ro; m->padmax = m->padding; m->nblocks = L;
+  FsmnArgs& a = m->fsmn;
+  memset(&a, 0, sizeof(a));
+  int rc = pack_common_front(m, &a.o_mean, &a.o_istd);
+  if (rc) return rc;
+  const int NP = fsmn_pass_cols();
+  auto npad = [&](int n) { return (n + NP - 1) / NP * NP; };
+  auto push_wt = [&](const float* W, int N, int K, int* off) {      // W[n][k] -> W^T [K][npad(N)]
+    *off = (int)m->h_vec.size();
+    const int np = npad(N);
+    m->h_vec.resize(m->h_vec.size() + (size_t)K * np, 0.f);
+    for (int k = 0; k < K; ++k)
+      for (int n = 0; n < N; ++n) m->h_vec[*off + (size_t)k * np + n] = W[(size_t)n * K + k];
+  };
+  auto push_b = [&](const float* b, int N, int* off) {
+    *off = (int)m->h_vec.size();
+    m->h_vec.resize(m->h_vec.size() + npad(N), 0.f);
+    for (int n = 0; n < N; ++n) m->h_vec[*off + n] = b[n];
+  };
+  GET(w1, "backbone.in_linear1.linear.weight", (size_t)A1 * idim);
+  GET(b1, "backbone.in_linear1.linear.bias", (size_t)A1);
+  GET(w2, "backbone.in_linear2.linear.weight", (size_t)D * A1);
+  GET(b2, "backbone.in_linear2.linear.bias", (size_t)D);
+  push_wt(w1, A1, idim, &a.o_w_in1); push_b(b1, A1, &a.o_b_in1);
+  push_wt(w2, D, A1, &a.o_w_in2); push_b(b2, D, &a.o_b_in2);
+  a.o_layers = (int)m->h_vec.size();
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "backbone.fsmn." + std::to_string(l) + ".";
+    GET(wp, p + "0.linear.weight", (size_t)P * D);
+    GET(wl, p + "1.conv_left.weight", (size_t)P * lo);
+    GET(wr, p + "1.conv_right.weight", (size_t)P * ro);
+    GET(wa, p + "2.linear.weight", (size_t)D * P);
+    GET(ba, p + "2.linear.bias", (size_t)D);
+    const int base = (int)m->h_vec.size();
+    int off;
+    push_wt(wp, P, D, &off);
+    if (l == 0) a.lo_wp = off - base;
+    off = (int)m->h_vec.size();
+    if (l == 0) a.lo_taps = off - base;
+    m->h_vec.resize(m->h_vec.size() + pad4((size_t)(lo + ro) * P), 0.f);
+    for (int i = 0; i < lo; ++i)
+      for (int ch = 0; ch < P; ++ch) m->h_vec[off + (size_t)i * P + ch] = wl[(size_t)ch * lo + i];
+    for (int j = 0; j < ro; ++j)
+      for (int ch = 0; ch < P; ++ch) m->h_vec[off + (size_t)(lo + j) * P + ch] = wr[(size_t)ch * ro + j];
+    push_wt(wa, D, P, &off);
+    if (l == 0) a.lo_wa = off - base;
+    push_b(ba, D, &off);
+    if (l == 0) a.lo_ba = off - base;
+    if (l == 0) a.layer_stride = (int)m->h_vec.size() - base;
+  }
+  GET(wo1, "backbone.out_linear1.linear.weight", (size_t)A2 * D);
+  GET(bo1, "backbone.out_linear1.linear.bias", (size_t)A2);
+  GET(wo2, "backbone.out_linear2.linear.weight", (size_t)O * A2);
+  GET(bo2, "backbone.out_linear2.linear.bias", (size_t)O);
+  push_wt(wo1, A2, D, &a.o_w_out1); push_b(bo1, A2, &a.o_b_out1);
+  push_wt(wo2, O, A2, &a.o_w_out2); push_b(bo2, O, &a.o_b_out2);
+  a.idim = idim; a.aff_in = A1; a.lin = D; a.proj = P; a.aff_out = A2; a.odim = O; a.L = L; a.lorder = lo; a.rorder = ro;
+  a.act = c.activation; a.has_cmvn = m->has_cmvn ? 1 : 0; a.norm_var = 1;      // istd already 1 when norm_var is off
+  a.np_aff_in = npad(A1); a.np_lin = npad(D); a.np_proj = npad(P); a.np_aff_out = npad(A2); a.np_odim = npad(O);
+  const int m0 = idim > D ? idim : D;
+  int m1 = A1 > P ? A1 : P;
+  if (A2 > m1) m1 = A2;
+  a.sp0 = (int)pad4(m0) + 4; a.sp1 = (int)pad4(m1) + 4; a.spm = (int)pad4(P) + 4;   // +4: rows start in different banks
+  WEKWS_REQUIRE(fsmn_smem_bytes(a) <= 227 * 1024, "fsmn: layer widths (%d, %d, %d) exceed the fused kernel's shared memory", m0, m1, P);
+  return WEKWS_OK;
+}
+
 void free_device(wekws_model* m) {
   cudaFree(m->d_stream); cudaFree(m->d_vec); cudaFree(m->d_chunk_off); cudaFree(m->d_wimg);
   m->d_stream = nullptr; m->d_vec = nullptr; m->d_chunk_off = nullptr; m->d_wimg = nullptr;
@@ -451,7 +532,7 @@ extern "C" uint64_t wekws_launch_count(void) { return g_launches.load(); }
 
 extern "C" int wekws_model_create(const wekws_model_config* cfg, wekws_model** out) {
   WEKWS_REQUIRE(cfg && out, "wekws_model_create: null argument");
-  WEKWS_REQUIRE(cfg->backbone >= WEKWS_BACKBONE_MDTC && cfg->backbone <= WEKWS_BACKBONE_GRU,
+  WEKWS_REQUIRE(cfg->backbone >= WEKWS_BACKBONE_MDTC && cfg->backbone <= WEKWS_BACKBONE_FSMN,
                 "unknown backbone id %d", cfg->backbone);
   WEKWS_REQUIRE(cfg->odim >= 1, "output_dim must be >= 1");
   WEKWS_REQUIRE(cfg->activation == WEKWS_ACT_IDENTITY || cfg->activation == WEKWS_ACT_SIGMOID,
@@ -472,6 +553,7 @@ extern "C" void wekws_model_destroy(wekws_model* m) {
 extern "C" int wekws_model_padding(const wekws_model* m) {
   if (!m) return 0;
   if (m->cfg.backbone == WEKWS_BACKBONE_GRU) return 0;
+  if (m->cfg.backbone == WEKWS_BACKBONE_FSMN) return m->cfg.fsmn_left_order - 1 + m->cfg.fsmn_right_order;
   int pad = 0;
   const int K = m->cfg.kernel_size;
   if (m->cfg.backbone == WEKWS_BACKBONE_MDTC) {
@@ -493,6 +575,7 @@ extern "C" int wekws_model_set_tensor(wekws_model* m, const char* name, const fl
 
 extern "C" int wekws_model_pack(wekws_model* m) {
   WEKWS_REQUIRE(m, "wekws_model_pack: null handle");
+  if (m->cfg.backbone == WEKWS_BACKBONE_FSMN) return pack_fsmn(m);
   return m->cfg.backbone == WEKWS_BACKBONE_GRU ? pack_gru(m) : pack_conv(m);
 }
 
@@ -504,7 +587,9 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
   WEKWS_CUDA_OK(cudaGetDevice(&m->device));
   WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_vec, m->h_vec.size() * sizeof(float)));
   WEKWS_CUDA_OK(cudaMemcpy(m->d_vec, m->h_vec.data(), m->h_vec.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (m->cfg.backbone != WEKWS_BACKBONE_GRU) {
+  if (m->cfg.backbone == WEKWS_BACKBONE_FSMN) {
+    m->fsmn.w = m->d_vec;
+  } else if (m->cfg.backbone != WEKWS_BACKBONE_GRU) {
     WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_stream, m->h_stream.size() * sizeof(float)));
     WEKWS_CUDA_OK(cudaMemcpy(m->d_stream, m->h_stream.data(), m->h_stream.size() * sizeof(float), cudaMemcpyHostToDevice));
     WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_chunk_off, m->h_chunk_off.size() * sizeof(int)));
@@ -567,7 +652,25 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
   WEKWS_CUDA_OK(cudaGetDevice(&dev));
   WEKWS_REQUIRE(dev == m->device, "model was finalized on device %d but current device is %d", m->device, dev);
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->cfg.backbone == WEKWS_BACKBONE_GRU) {
+  if (m->cfg.backbone == WEKWS_BACKBONE_FSMN) {
+    // time-chunk to the tile height; the cache carries the memory-block state between chunks exactly as in streaming use
+    const int maxT = fsmn_tile_rows();
+    const int nchunk = (int)((T + maxT - 1) / maxT);
+    const int Tc = (int)((T + nchunk - 1) / nchunk);
+    for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+      FsmnArgs a = m->fsmn;
+      a.feats = d_feats + t0 * m->cfg.idim;
+      a.out = d_out + t0 * m->cfg.odim;
+      a.in_cache = t0 == 0 ? d_in_cache : d_out_cache;
+      a.out_cache = d_out_cache;
+      a.B = (int)B;
+      a.T = (int)(T - t0 < Tc ? T - t0 : Tc);
+      a.feat_bstride = T * m->cfg.idim;
+      a.out_bstride = T * m->cfg.odim;
+      int rc = fsmn_launch(a, st);
+      if (rc) return rc;
+    }
+  } else if (m->cfg.backbone == WEKWS_BACKBONE_GRU) {
     GruArgs a = m->gru;
     a.feats = d_feats; a.in_cache = d_in_cache; a.out = d_out; a.out_cache = d_out_cache;
     a.B = (int)B; a.T = (int)T;

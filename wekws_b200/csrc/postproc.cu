@@ -64,3 +64,54 @@ extern "C" int wekws_det_stats(const float* d_post, const int32_t* d_lens, int64
       d_post, d_lens, B, T, K, d_thresholds, nthr, window_shift, d_max_score, d_triggers);
   return check_launch("det_stats_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Input transforms of the FSMN / CTC recipes: context expansion + frame skipping, i.e.
+// wekws/dataset/processor.py:267-312 (context_expansion, frame_skip; batched twin wekws/dataset/init_dataset.py:24-68):
+//   ctx[t] = concat(feats[max(t - left, 0)], ..., feats[t], ..., feats[t + right])   for t < n - right
+//   (the roll() wrap-around on the left is overwritten by the first frame -- "replication pad left margin" -- and the
+//   last `right` frames are dropped, so nothing ever wraps), then every skip_rate-th frame is kept.
+namespace wekws {
+namespace {
+__global__ void context_expand_kernel(const float* __restrict__ feats, const int32_t* __restrict__ lens, long long B,
+                                      long long T, int D, int left, int right, int skip, float* __restrict__ out,
+                                      long long out_frames) {
+  const int W = left + right + 1;
+  const long long row = blockIdx.x;                 // (b, i)
+  const long long b = row / out_frames, i = row - b * out_frames;
+  long long n = lens ? (long long)lens[b] : T;
+  n = n < 0 ? 0 : (n > T ? T : n);
+  const long long kept = n > right ? (n - right + skip - 1) / skip : 0;
+  float* o = out + row * (long long)W * D;
+  const float* f = feats + b * T * D;
+  for (int e = threadIdx.x; e < W * D; e += blockDim.x) {
+    float v = 0.f;
+    if (i < kept) {
+      const int idx = e / D, d = e - idx * D;
+      long long t = i * skip + idx - left;
+      if (t < 0) t = 0;
+      v = f[t * D + d];
+    }
+    o[e] = v;
+  }
+}
+}  // namespace
+}  // namespace wekws
+
+extern "C" int64_t wekws_context_expand_frames(int64_t num_frames, int right, int skip) {
+  if (skip < 1 || right < 0 || num_frames <= right) return 0;
+  return (num_frames - right + skip - 1) / skip;
+}
+
+extern "C" int wekws_context_expand(const float* d_feats, const int32_t* d_lens, int64_t B, int64_t T, int D, int left,
+                                    int right, int skip, float* d_out, int64_t out_frames, void* stream) {
+  WEKWS_REQUIRE(B >= 0 && T >= 0 && D >= 1 && left >= 0 && right >= 0 && skip >= 1, "wekws_context_expand: bad sizes");
+  WEKWS_REQUIRE(out_frames >= wekws_context_expand_frames(T, right, skip), "wekws_context_expand: out_frames %lld too small",
+                (long long)out_frames);
+  if (B == 0 || out_frames == 0) return WEKWS_OK;
+  WEKWS_REQUIRE(d_out && (d_feats || T == 0), "wekws_context_expand: null argument");
+  WEKWS_REQUIRE(B * out_frames < (1ll << 31), "wekws_context_expand: too many output rows");
+  context_expand_kernel<<<(unsigned)(B * out_frames), 128, 0, (cudaStream_t)stream>>>(d_feats, d_lens, B, T, D, left,
+                                                                                     right, skip, d_out, out_frames);
+  return check_launch("context_expand_kernel");
+}

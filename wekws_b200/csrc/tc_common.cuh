@@ -219,6 +219,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // all tcgen05 ops issued so far by this thread arrive on `bar` when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -237,6 +244,73 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane; the caller issues tmem_ld_wait() before using them
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------- packed f32x2 math (FFMA2 / FADD2)
+// Two fp32 values in one 64-bit register (lo = first).  fma.rn.f32x2 issues ONE instruction for two FMAs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 16-byte shared-memory accesses as two packed pairs (shared-window addresses)
+__device__ __forceinline__ void lds_2x2(uint32_t addr, f32x2& a, f32x2& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_2x2(uint32_t addr, f32x2 a, f32x2 b) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
+
+// bf16 split of a packed pair, 5 instructions: hi = bf16x2(x) (1), its two values back as fp32 (2), the exact
+// residual r = x - hi with one packed FMA (1), lo = bf16x2(r) (1).
+//   split_pair_rn      : hi rounded to nearest (|r| <= 2^-9 |x|), no activation
+//   split_pair_rz_relu : y = max(x, 0) folded in: hi = RZ(relu(x)) via cvt.rz.relu, so r = x - hi keeps the sign of x
+//                        (r >= 0 for x >= 0, r = x < 0 for x < 0) and lo = RN(relu(r)) -- no separate max
+__device__ __forceinline__ void split_pair_rn(f32x2 x, uint32_t& hi, uint32_t& lo) {
+  float x0, x1, r0, r1;
+  unpack2(x, x0, x1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const f32x2 hf = pack2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  const f32x2 neg1 = 0xbf800000bf800000ull;                   // {-1.0f, -1.0f}
+  unpack2(fma2(hf, neg1, x), r0, r1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void split_pair_rz_relu(f32x2 x, uint32_t& hi, uint32_t& lo) {
+  float x0, x1, r0, r1;
+  unpack2(x, x0, x1);
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const f32x2 hf = pack2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  const f32x2 neg1 = 0xbf800000bf800000ull;
+  unpack2(fma2(hf, neg1, x), r0, r1);
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 // UMMA instruction descriptor: bf16 A/B (K-major), fp32 accumulate, M x N  (cute mma_sm100_desc.hpp:412-434)

@@ -5,7 +5,7 @@ The reference ships models to its C++ runtime as ONNX (wekws/bin/export_onnx.py:
 graph -- the network is the fused kernels -- only the configuration and the tensors of the reference
 ``state_dict`` under their reference keys, which is what a ``.wkb`` file holds:
 
-    "WKB1" | int32 version (1) | wekws_model_config (10 x int32) | int32 ntensors |
+    "WKB1" | int32 version (2) | int32 nconfig | wekws_model_config (nconfig x int32) | int32 ntensors |
     ntensors x ( int32 name_len | name | int64 numel | numel x float32 )        (little endian)
 """
 from __future__ import annotations
@@ -14,7 +14,7 @@ import struct
 
 import torch
 
-MAGIC, VERSION = b"WKB1", 1
+MAGIC, VERSION = b"WKB1", 2
 
 
 def export_native(model, path: str) -> dict:
@@ -27,6 +27,7 @@ def export_native(model, path: str) -> dict:
     with open(path, "wb") as f:
         f.write(MAGIC)
         f.write(struct.pack("<i", VERSION))
+        f.write(struct.pack("<i", len(fields)))
         f.write(struct.pack("<%di" % len(fields), *fields))
         f.write(struct.pack("<i", len(tensors)))
         for name, t in tensors:
@@ -35,7 +36,10 @@ def export_native(model, path: str) -> dict:
             f.write(raw)
             f.write(struct.pack("<q", t.numel()))
             f.write(t.numpy().tobytes())
-    return {"cache_dim": model.hdim, "cache_len": getattr(model.backbone, "padding", 0), "tensors": len(tensors)}
+    fsmn = getattr(model.backbone, "kind", None) == "fsmn"
+    return {"cache_dim": model.backbone.proj_dim if fsmn else model.hdim,
+            "cache_len": model.backbone.cache_len if fsmn else getattr(model.backbone, "padding", 0),
+            "tensors": len(tensors)}
 
 
 def read_native(path: str):
@@ -46,7 +50,8 @@ def read_native(path: str):
     off = 4
     (version,) = struct.unpack_from("<i", data, off); off += 4
     assert version == VERSION
-    fields = struct.unpack_from("<10i", data, off); off += 40
+    (nconfig,) = struct.unpack_from("<i", data, off); off += 4
+    fields = struct.unpack_from("<%di" % nconfig, data, off); off += 4 * nconfig
     (n,) = struct.unpack_from("<i", data, off); off += 4
     out = {}
     for _ in range(n):

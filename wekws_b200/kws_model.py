@@ -104,6 +104,40 @@ def _tcn(num_layers: int, ch: int, k: int, dropout: float, ds: bool) -> nn.Modul
     return bb
 
 
+def _affine(idim: int, odim: int, bias: bool = True) -> nn.Module:
+    """AffineTransform / LinearTransform: state_dict linear.{weight[,bias]} (fsmn.py:56-60, 114-118)."""
+    return _holder(linear=nn.Linear(idim, odim, bias=bias))
+
+
+def _fsmn(input_dim: int, input_affine_dim: int, fsmn_layers: int, linear_dim: int, proj_dim: int, lorder: int,
+          rorder: int, lstride: int, rstride: int, output_affine_dim: int, output_dim: int) -> nn.Module:
+    """Parameter holder with the key set of wekws/model/fsmn.py FSMN (fsmn.py:401-456): in_linear{1,2}.linear.*,
+    fsmn.{l}.0.linear.weight (LinearTransform, no bias), fsmn.{l}.1.conv_{left,right}.weight (FSMNBlock: depthwise
+    Conv2d (proj,1,order,1), no bias), fsmn.{l}.2.linear.* (AffineTransform), out_linear{1,2}.linear.*.  The blocks
+    are built with strides (1, 1) whatever the config says, exactly as _build_repeats does (fsmn.py:384-391);
+    lstride / rstride only enter `padding`."""
+    if rorder < 1:
+        raise NotImplementedError("wekws_b200: FSMN right_order must be >= 1 (the reference's FSMNBlock.forward itself "
+                                  "fails for right_order = 0, fsmn.py:235)")
+    layers = []
+    for _ in range(fsmn_layers):
+        mem = _holder(conv_left=nn.Conv2d(proj_dim, proj_dim, [lorder, 1], dilation=[1, 1], groups=proj_dim, bias=False),
+                      conv_right=nn.Conv2d(proj_dim, proj_dim, [rorder, 1], dilation=[1, 1], groups=proj_dim, bias=False))
+        layers.append(nn.Sequential(_affine(linear_dim, proj_dim, bias=False), mem, _affine(proj_dim, linear_dim),
+                                    nn.Module()))
+    bb = _holder(in_linear1=_affine(input_dim, input_affine_dim), in_linear2=_affine(input_affine_dim, linear_dim),
+                 relu=nn.Module(), fsmn=nn.Sequential(*layers), out_linear1=_affine(linear_dim, output_affine_dim),
+                 out_linear2=_affine(output_affine_dim, output_dim))
+    bb.kind = "fsmn"
+    bb.input_dim, bb.input_affine_dim, bb.fsmn_layers, bb.linear_dim, bb.proj_dim = \
+        input_dim, input_affine_dim, fsmn_layers, linear_dim, proj_dim
+    bb.lorder, bb.rorder, bb.lstride, bb.rstride = lorder, rorder, lstride, rstride
+    bb.output_affine_dim, bb.output_dim = output_affine_dim, output_dim
+    bb.padding = (lorder - 1) * lstride + rorder * rstride          # fsmn.py:443-444 (API attribute)
+    bb.cache_len = (lorder - 1) + rorder                            # what the blocks really keep (strides 1, 1)
+    return bb
+
+
 def _linear_classifier(idim: int, odim: int) -> nn.Module:
     """state_dict: linear.{weight,bias} (classifier.py:57-61)."""
     return _holder(linear=nn.Linear(idim, odim))
@@ -178,6 +212,14 @@ class KWSModel(nn.Module):
         elif getattr(bb, "kind", None) in ("tcn", "ds_tcn"):
             cfg.backbone = _native.BACKBONE_DSTCN if bb.ds else _native.BACKBONE_TCN
             cfg.num_layers, cfg.kernel_size = bb.num_layers, bb.kernel_size
+        elif getattr(bb, "kind", None) == "fsmn":
+            if self.preprocessing is not None and not getattr(self.preprocessing, "is_identity", False):
+                raise NotImplementedError("wekws_b200: FSMN runs with preprocessing type 'none' (as every shipped config)")
+            if not isinstance(self.classifier, nn.Identity):
+                raise NotImplementedError("wekws_b200: FSMN runs with classifier type 'identity' (as every shipped config)")
+            cfg.backbone, cfg.num_layers = _native.BACKBONE_FSMN, bb.fsmn_layers
+            cfg.fsmn_input_affine_dim, cfg.fsmn_linear_dim, cfg.fsmn_proj_dim = bb.input_affine_dim, bb.linear_dim, bb.proj_dim
+            cfg.fsmn_left_order, cfg.fsmn_right_order, cfg.fsmn_output_affine_dim = bb.lorder, bb.rorder, bb.output_affine_dim
         else:
             raise NotImplementedError(f"wekws_b200: backbone {type(bb).__name__} has no fused kernel")
         if isinstance(self.activation, nn.Sigmoid):
@@ -252,7 +294,12 @@ class KWSModel(nn.Module):
         if not x.is_contiguous():
             x = x.contiguous()
         gru = isinstance(self.backbone, nn.GRU)
-        cache_shape = (self.backbone.num_layers, B, self.hdim) if gru else (B, self.hdim, self.backbone.padding)
+        if gru:
+            cache_shape = (self.backbone.num_layers, B, self.hdim)
+        elif getattr(self.backbone, "kind", None) == "fsmn":      # 4-D: one column block per layer (fsmn.py:488)
+            cache_shape = (B, self.backbone.proj_dim, self.backbone.cache_len, self.backbone.fsmn_layers)
+        else:
+            cache_shape = (B, self.hdim, self.backbone.padding)
         cache_ptr = None
         if in_cache is not None and in_cache.numel() > 0:
             if tuple(in_cache.shape) != cache_shape:
@@ -315,9 +362,12 @@ def init_model(configs: dict) -> KWSModel:
     prep_type = configs["preprocessing"]["type"]
     if prep_type == "linear":
         preprocessing = _linear_subsampling(input_dim, hidden_dim)
+    elif prep_type == "none" and configs["backbone"]["type"] == "fsmn":
+        preprocessing = nn.Module()          # NoSubsampling (subsampling.py:28-39): identity, no parameters
+        preprocessing.subsampling_rate, preprocessing.is_identity = 1, True
     elif prep_type in ("cnn1d_s1", "none"):
         raise NotImplementedError(f"wekws_b200: preprocessing type '{prep_type}' is outside the fused hot path "
-                                  "(SURVEY.md section 2 row 4); only 'linear' is implemented")
+                                  "(SURVEY.md section 2 row 4); 'linear' (and 'none' in front of FSMN) are implemented")
     else:
         print("Unknown preprocessing type {}".format(prep_type))
         sys.exit(1)
@@ -332,18 +382,34 @@ def init_model(configs: dict) -> KWSModel:
         hidden_dim = bb["hidden_dim"]
         assert bb["causal"] is True, "we now only support causal mdtc"
         backbone = _mdtc(bb["num_stack"], bb["stack_size"], hidden_dim, bb["kernel_size"])
-    elif bb["type"] == "fsmn":
-        raise NotImplementedError("wekws_b200: the FSMN backbone is outside the fused hot path "
-                                  "(SURVEY.md section 8f row f4)")
+    elif bb["type"] == "fsmn":                                  # kws_model.py:158-170
+        backbone = _fsmn(input_dim, bb["input_affine_dim"], bb["num_layers"], bb["linear_dim"], bb["proj_dim"],
+                         bb["left_order"], bb["right_order"], bb["left_stride"], bb["right_stride"],
+                         bb["output_affine_dim"], output_dim)
     else:
         print("Unknown body type {}".format(bb["type"]))
         sys.exit(1)
 
-    if "classifier" in configs:
-        raise NotImplementedError("wekws_b200: the speech-command 'classifier' heads (global/last) are "
-                                  "outside the streaming hot path (SURVEY.md section 2 row 8)")
-    classifier = _linear_classifier(hidden_dim, output_dim)
     activation: nn.Module = nn.Sigmoid()
+    if "classifier" in configs:                                 # kws_model.py:175-195
+        classifier_type = configs["classifier"]["type"]
+        if classifier_type in ("global", "last"):
+            raise NotImplementedError("wekws_b200: the speech-command 'classifier' heads (global/last) are "
+                                      "outside the streaming hot path (SURVEY.md section 2 row 8)")
+        elif classifier_type == "identity":
+            if bb["type"] != "fsmn":
+                raise NotImplementedError("wekws_b200: classifier 'identity' is implemented behind the FSMN backbone "
+                                          "(the only shipped use, fsmn_ctc.yaml)")
+            classifier: nn.Module = nn.Identity()
+        else:
+            print("Unknown classifier type {}".format(classifier_type))
+            sys.exit(1)
+        activation = nn.Identity()
+    else:
+        if bb["type"] == "fsmn":
+            raise NotImplementedError("wekws_b200: FSMN needs classifier type 'identity' (its out_linear2 already maps "
+                                      "to output_dim, fsmn_ctc.yaml:53-55)")
+        classifier = _linear_classifier(hidden_dim, output_dim)
     if "activation" in configs:
         if configs["activation"]["type"] == "identity":
             activation = nn.Identity()

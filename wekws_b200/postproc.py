@@ -63,3 +63,30 @@ def det_curve(thresholds, max_score, triggers, is_keyword, filler_hours: float, 
         fa = num_false_alarm / filler_hours if filler_hours else 0.0
         rows.append((th, fa, frr))
     return rows
+
+
+def context_expansion(feats: torch.Tensor, left: int = 1, right: int = 1, skip_rate: int = 1,
+                      lengths: Optional[torch.Tensor] = None):
+    """wekws/dataset/processor.py:267-312 (context_expansion then frame_skip) on the device, batched:
+    feats (B, T, D) float32 CUDA [, lengths (B,)] -> (expanded (B, m, D*(left+right+1)), new_lengths (B,) int32) with
+    m = ceil((T - right) / skip_rate); stream b keeps ceil((lengths[b] - right) / skip_rate) rows, the rest are zero
+    (the zero padding pad_sequence would add)."""
+    if not feats.is_cuda:
+        raise RuntimeError("wekws_b200.context_expansion runs on CUDA only; got a CPU tensor (no CPU fallback)")
+    if feats.dim() != 3 or feats.dtype != torch.float32:
+        raise ValueError("feats must be a (B, T, D) float32 tensor")
+    feats = feats.contiguous()
+    B, T, D = feats.shape
+    lib = _native.lib()
+    m = int(lib.wekws_context_expand_frames(T, int(right), int(skip_rate)))
+    out = torch.empty(B, m, D * (left + right + 1), device=feats.device, dtype=torch.float32)
+    lens = None if lengths is None else lengths.to(device=feats.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(feats.device):
+        rc = lib.wekws_context_expand(
+            C.c_void_p(feats.data_ptr()), C.c_void_p(lens.data_ptr()) if lens is not None else None, B, T, D, int(left),
+            int(right), int(skip_rate), C.c_void_p(out.data_ptr()), m,
+            C.c_void_p(torch.cuda.current_stream(feats.device).cuda_stream))
+    _native.check(rc, "wekws_context_expand")
+    n = torch.full((B,), T, dtype=torch.int64) if lengths is None else lengths.detach().cpu().to(torch.int64)
+    new_len = torch.where(n > right, (n - right + skip_rate - 1) // skip_rate, torch.zeros_like(n)).to(torch.int32)
+    return out, new_len

@@ -35,16 +35,24 @@ T ReadPod(std::ifstream& is, const char* what) {
 
 }  // namespace
 
-// .wkb layout (little endian): "WKB1", int32 version = 1, wekws_model_config (10 x int32), int32 ntensors, then per
-// tensor: int32 name_len, name bytes, int64 numel, numel x float32.
+// .wkb layout (little endian): "WKB1", int32 version = 2, int32 nconfig, wekws_model_config (nconfig x int32; missing
+// trailing fields of an older, shorter config block are zero), int32 ntensors, then per tensor: int32 name_len, name
+// bytes, int64 numel, numel x float32.
 KeywordSpotting::KeywordSpotting(const std::string& model_path) {
   std::ifstream is(model_path, std::ios::binary);
   if (!is) Fatal("cannot open model file", model_path.c_str());
   char magic[4];
   is.read(magic, 4);
   if (!is || memcmp(magic, "WKB1", 4) != 0) Fatal("not a wekws_b200 native model file (.wkb)", model_path.c_str());
-  if (ReadPod<int32_t>(is, "version") != 1) Fatal("unsupported .wkb version", model_path.c_str());
-  const wekws_model_config cfg = ReadPod<wekws_model_config>(is, "config");
+  if (ReadPod<int32_t>(is, "version") != 2) Fatal("unsupported .wkb version", model_path.c_str());
+  const int32_t nconfig = ReadPod<int32_t>(is, "config length");
+  if (nconfig < 10 || nconfig > 64) Fatal("corrupt config block", model_path.c_str());
+  wekws_model_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  for (int32_t i = 0; i < nconfig; ++i) {
+    const int32_t v = ReadPod<int32_t>(is, "config");
+    if (i < (int32_t)(sizeof(cfg) / sizeof(int32_t))) reinterpret_cast<int32_t*>(&cfg)[i] = v;
+  }
   AbiOk(wekws_model_create(&cfg, &model_), "wekws_model_create");
   const int32_t ntensors = ReadPod<int32_t>(is, "tensor count");
   std::vector<float> buf;
@@ -63,11 +71,12 @@ KeywordSpotting::KeywordSpotting(const std::string& model_path) {
   AbiOk(wekws_model_finalize(model_), "wekws_model_finalize");      // folds BatchNorm, packs, uploads
   idim_ = cfg.idim;
   odim_ = cfg.odim;
-  cache_dim_ = cfg.hdim;
+  cache_dim_ = cfg.backbone == WEKWS_BACKBONE_FSMN ? cfg.fsmn_proj_dim : cfg.hdim;
   cache_len_ = wekws_model_padding(model_);
-  // conv backbones: (1, hidden_dim, padding); GRU: (num_layers, 1, hidden_dim)
-  cache_floats_ = cfg.backbone == WEKWS_BACKBONE_GRU ? (long long)cfg.num_layers * cfg.hdim
-                                                     : (long long)cfg.hdim * cache_len_;
+  // conv backbones: (1, hidden_dim, padding); GRU: (num_layers, 1, hidden_dim); FSMN: (1, proj_dim, padding, num_layers)
+  cache_floats_ = cfg.backbone == WEKWS_BACKBONE_GRU    ? (long long)cfg.num_layers * cfg.hdim
+                  : cfg.backbone == WEKWS_BACKBONE_FSMN ? (long long)cfg.fsmn_proj_dim * cache_len_ * cfg.num_layers
+                                                        : (long long)cfg.hdim * cache_len_;
   cudaStream_t st;
   CudaOk(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
   stream_ = st;
