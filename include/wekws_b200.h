@@ -187,6 +187,35 @@ WEKWS_API int wekws_det_stats(const float* d_post, const int32_t* d_lens, int64_
                     const double* d_thresholds, int nthr, int window_shift, double* d_max_score,
                     int32_t* d_triggers, void* stream);
 
+/* CTC prefix beam search + keyword look-up on the device (CTC models), bit-exact with the reference's pure
+ * Python: wekws/model/loss.py:206-312 ctc_prefix_beam_search as called by wekws/bin/score_ctc.py:198-200 (whole
+ * utterance) and its per-frame streaming twin wekws/bin/stream_kws_ctc.py:124-215,400-409 (hypotheses carried in
+ * d_state between calls; frame numbers = frame_offset + row * frame_stride), then the look-up of
+ * score_ctc.py:201-220 / stream_kws_ctc.py:411-434.
+ *   d_probs (B,T,V) softmax posteriors; d_lens NULL = T frames; d_keyword_tokens: the keywords' token-id set
+ *   (n = 0: no filter); d_state: B x wekws_ctc_state_bytes() bytes or NULL (reset_state != 0: start from the empty
+ *   hypothesis and write the final state).
+ * Outputs per utterance, hypotheses in beam order: d_nhyp (B); d_hyp_len (B,path_beam) (-1 = unused);
+ *   d_hyp_tokens / d_node_frame / d_node_prob (B,path_beam,WEKWS_CTC_MAX_PREFIX); d_hyp_score (B,path_beam) = pb + pnb
+ *   (double, as Python computes it); d_overflow (B) != 0 if a prefix outgrew WEKWS_CTC_MAX_PREFIX tokens.          */
+#define WEKWS_CTC_MAX_PREFIX 64
+#define WEKWS_CTC_MAX_PATH_BEAM 20
+#define WEKWS_CTC_MAX_SCORE_BEAM 3
+WEKWS_API int64_t wekws_ctc_state_bytes(void);
+WEKWS_API int wekws_ctc_prefix_beam_search(const float* d_probs, const int32_t* d_lens, int64_t B, int64_t T, int V,
+                                 const int32_t* d_keyword_tokens, int n_keyword_tokens, int score_beam_size,
+                                 int path_beam_size, int64_t frame_offset, int frame_stride, void* d_state,
+                                 int reset_state, int32_t* d_nhyp, int32_t* d_hyp_len, int32_t* d_hyp_tokens,
+                                 double* d_hyp_score, int32_t* d_node_frame, float* d_node_prob, int32_t* d_overflow,
+                                 void* stream);
+/* d_kw_tokens: the keywords' token sequences back to back, keyword k = [d_kw_offsets[k], d_kw_offsets[k+1]).
+ * d_hit (B) = index of the detected keyword or -1; d_hit_score = sqrt(product of its token probabilities);
+ * d_start / d_end = frames of its first / last token.                                                        */
+WEKWS_API int wekws_ctc_keyword_hit(const int32_t* d_nhyp, const int32_t* d_hyp_len, const int32_t* d_hyp_tokens,
+                          const int32_t* d_node_frame, const float* d_node_prob, int64_t B, int path_beam_size,
+                          const int32_t* d_kw_tokens, const int32_t* d_kw_offsets, int num_keywords, int32_t* d_hit,
+                          double* d_hit_score, int32_t* d_start, int32_t* d_end, void* stream);
+
 /* Context expansion + frame skipping of the FSMN / CTC recipes: wekws/dataset/processor.py:267-312
  * (batched twin wekws/dataset/init_dataset.py:24-68).  d_feats (B,T,D); d_lens NULL = all T frames valid;
  * d_out (B, out_frames, D*(left+right+1)): row i of stream b = concat(feats[max(i*skip+k-left, 0)], k = 0..left+right)

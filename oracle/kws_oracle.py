@@ -438,3 +438,110 @@ def context_expansion(feats: Tensor, left: int = 1, right: int = 1) -> Tensor:
 def frame_skip(feats: Tensor, skip_rate: int = 1) -> Tensor:
     """wekws/dataset/processor.py:299-312."""
     return feats[::skip_rate, :]
+
+
+# ---------------------------------------------------------------------------- CTC prefix beam search + keyword look-up
+def ctc_prefix_beam_search(probs: Tensor, keywords_tokenset=None, score_beam_size: int = 3, path_beam_size: int = 20,
+                           cur_hyps=None, frame_offset: int = 0, frame_stride: int = 1):
+    """Restatement of wekws/model/loss.py:206-312 (same statements in the same order, incl. the shared node dicts), with
+    the streaming twin's extras (wekws/bin/stream_kws_ctc.py:124-215,400-409): hypotheses can be carried in and frames
+    are numbered frame_offset + t * frame_stride.  probs (T, V).  Returns the pruned cur_hyps list
+    [(prefix, (pb, pnb, nodes))]; hyps_of() gives loss.py's return value.  Pinned by tests/golden/ctc.npz."""
+    import math
+    from collections import defaultdict
+    if cur_hyps is None:
+        cur_hyps = [(tuple(), (1.0, 0.0, []))]
+    for row in range(probs.size(0)):
+        t = frame_offset + row * frame_stride
+        p = probs[row]
+        next_hyps = defaultdict(lambda: (0.0, 0.0, []))
+        top_k_probs, top_k_index = p.topk(score_beam_size)
+        filter_index = []
+        for prob, idx in zip(top_k_probs.tolist(), top_k_index.tolist()):
+            if prob > 0.05 and (keywords_tokenset is None or idx in keywords_tokenset):
+                filter_index.append(idx)
+        if len(filter_index) == 0:
+            continue
+        for s in filter_index:
+            ps = p[s].item()
+            for prefix, (pb, pnb, cur_nodes) in cur_hyps:
+                last = prefix[-1] if len(prefix) > 0 else None
+                if s == 0:
+                    n_pb, n_pnb, nodes = next_hyps[prefix]
+                    n_pb = n_pb + pb * ps + pnb * ps
+                    nodes = cur_nodes.copy()
+                    next_hyps[prefix] = (n_pb, n_pnb, nodes)
+                elif s == last:
+                    if not math.isclose(pnb, 0.0, abs_tol=0.000001):
+                        n_pb, n_pnb, nodes = next_hyps[prefix]
+                        n_pnb = n_pnb + pnb * ps
+                        nodes = cur_nodes.copy()
+                        if ps > nodes[-1]['prob']:
+                            nodes[-1]['prob'] = ps
+                            nodes[-1]['frame'] = t
+                        next_hyps[prefix] = (n_pb, n_pnb, nodes)
+                    if not math.isclose(pb, 0.0, abs_tol=0.000001):
+                        n_prefix = prefix + (s, )
+                        n_pb, n_pnb, nodes = next_hyps[n_prefix]
+                        n_pnb = n_pnb + pb * ps
+                        nodes = cur_nodes.copy()
+                        nodes.append(dict(token=s, frame=t, prob=ps))
+                        next_hyps[n_prefix] = (n_pb, n_pnb, nodes)
+                else:
+                    n_prefix = prefix + (s, )
+                    n_pb, n_pnb, nodes = next_hyps[n_prefix]
+                    if nodes:
+                        if ps > nodes[-1]['prob']:
+                            nodes.pop()
+                            nodes.append(dict(token=s, frame=t, prob=ps))
+                    else:
+                        nodes = cur_nodes.copy()
+                        nodes.append(dict(token=s, frame=t, prob=ps))
+                    n_pnb = n_pnb + pb * ps + pnb * ps
+                    next_hyps[n_prefix] = (n_pb, n_pnb, nodes)
+        next_hyps = sorted(next_hyps.items(), key=lambda x: (x[1][0] + x[1][1]), reverse=True)
+        cur_hyps = next_hyps[:path_beam_size]
+    return cur_hyps
+
+
+def hyps_of(cur_hyps):
+    """loss.py:311: [(prefix, pb + pnb, nodes)]."""
+    return [(y[0], y[1][0] + y[1][1], y[1][2]) for y in cur_hyps]
+
+
+def is_sublist(main_list, check_list):
+    """wekws/bin/score_ctc.py:88-103, verbatim behaviour (the last offset is never tried for a longer main list)."""
+    if len(main_list) < len(check_list):
+        return -1
+    if len(main_list) == len(check_list):
+        return 0 if tuple(main_list) == tuple(check_list) else -1
+    for i in range(len(main_list) - len(check_list)):
+        if main_list[i] == check_list[0]:
+            for j in range(len(check_list)):
+                if main_list[i + j] != check_list[j]:
+                    break
+            else:
+                return i
+    return -1
+
+
+def ctc_keyword_hit(hyps, keywords_token):
+    """wekws/bin/score_ctc.py:201-220 -> (word or None, hit_score, start, end)."""
+    import math
+    hit_keyword, hit_score, start, end = None, 1.0, 0, 0
+    for one_hyp in hyps:
+        prefix_ids, prefix_nodes = one_hyp[0], one_hyp[2]
+        for word in keywords_token.keys():
+            lab = keywords_token[word]['token_id']
+            offset = is_sublist(prefix_ids, lab)
+            if offset != -1:
+                hit_keyword = word
+                start = prefix_nodes[offset]['frame']
+                end = prefix_nodes[offset + len(lab) - 1]['frame']
+                for idx in range(offset, offset + len(lab)):
+                    hit_score *= prefix_nodes[idx]['prob']
+                break
+        if hit_keyword is not None:
+            hit_score = math.sqrt(hit_score)
+            break
+    return hit_keyword, hit_score, start, end

@@ -286,3 +286,80 @@ def test_context_expansion_and_frame_skip_bit_exact():
         want = O.frame_skip(O.context_expansion(x[b, :lens[b]], 2, 2), 3) if lens[b] > 2 else torch.zeros(0, 400)
         assert int(n[b]) == want.shape[0]
         assert torch.equal(y[b, :want.shape[0]].cpu(), want) and float(y[b, want.shape[0]:].abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------- CTC prefix beam search
+KEYWORDS_TOKEN = {"hi_xiaowen": {"token_id": [5, 9, 17, 23]}, "nihao_wenwen": {"token_id": [31, 7, 23, 23]}}
+
+
+def test_ctc_prefix_beam_search_bit_exact_with_reference_golden(tmp_path):
+    """Device decoder == the hypotheses returned by the reference's own loss.py ctc_prefix_beam_search (golden) and the
+    oracle: beam order, prefixes, pb + pnb as doubles (exact), node frames / probabilities; ragged batch; chunked
+    decoding with carried state == whole utterance; keyword look-up and the score_ctc.py score lines."""
+    import io
+    from tests.test_oracle_pinned import _ctc_golden_cases
+    from wekws_b200 import ctc_keyword_hits, ctc_prefix_beam_search, ctc_state, write_ctc_scores
+    cases = list(_ctc_golden_cases())
+    for use_set in (True, False):
+        sel = [c for c in cases if (c[2] is not None) == use_set]
+        if not sel:
+            continue
+        tokenset = sel[0][2]
+        Tm = max(c[1].size(0) for c in sel)
+        V = sel[0][1].size(1)
+        probs = torch.zeros(len(sel), Tm, V)
+        lens = torch.tensor([c[1].size(0) for c in sel], dtype=torch.int32)
+        for k, c in enumerate(sel):
+            probs[k, :c[1].size(0)] = c[1]
+        res = ctc_prefix_beam_search(probs.to(DEV), lens, tokenset)
+        assert int(res.overflow.sum()) == 0
+        got = res.to_python()
+        for k, c in enumerate(sel):
+            assert got[k] == c[3], (use_set, c[0])
+        # chunked with carried hypotheses (the streaming caller, stream_kws_ctc.py:482-501)
+        st = ctc_state(len(sel), DEV)
+        for t0 in range(0, Tm, 23):
+            part = probs[:, t0:t0 + 23]
+            r2 = ctc_prefix_beam_search(part.to(DEV), (lens - t0).clamp(0, part.size(1)), tokenset, state=st,
+                                        reset_state=(t0 == 0), frame_offset=t0)
+        assert r2.to_python() == got
+        # keyword look-up + score file
+        hits = ctc_keyword_hits(res, KEYWORDS_TOKEN)
+        want = [O.ctc_keyword_hit(c[3], KEYWORDS_TOKEN) for c in sel]
+        assert hits == want
+        a, b = io.StringIO(), io.StringIO()
+        write_ctc_scores(a, ["utt%d" % k for k in range(len(sel))], hits)
+        for k, (word, sc, _, _) in enumerate(want):                   # score_ctc.py:217-226
+            b.write('{} detected {} {:.3f}\n'.format("utt%d" % k, word, sc) if word is not None else '{} rejected\n'.format("utt%d" % k))
+        assert a.getvalue() == b.getvalue()
+
+
+def test_ctc_decode_large_vocabulary_matches_oracle():
+    """Vocabulary 2599 (the shipped CTC token list size), 64 utterances: device decoder == oracle restatement."""
+    from wekws_b200 import ctc_keyword_hits, ctc_prefix_beam_search
+    g = torch.Generator().manual_seed(17)
+    B, T, V = 64, 80, 2599
+    kw = {"kw_a": {"token_id": [100, 2000, 57]}, "kw_b": {"token_id": [2598, 100]}}
+    tokenset = {0, 100, 2000, 57, 2598}
+    logits = torch.randn(B, T, V, generator=g) * 0.3
+    dom = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        t = int(torch.randint(0, 10, (1,), generator=g))
+        for tok in ([100, 2000, 57] if b % 3 else [2598, 100, 2000, 57, 57]):
+            for _ in range(int(torch.randint(1, 4, (1,), generator=g))):
+                if t < T:
+                    dom[b, t] = tok
+                    t += 1
+            t += int(torch.randint(0, 3, (1,), generator=g))
+    logits.scatter_add_(2, dom.unsqueeze(2), torch.full((B, T, 1), 12.0))
+    probs = logits.softmax(2)
+    res = ctc_prefix_beam_search(probs.to(DEV), None, tokenset)
+    got = res.to_python()
+    hits = ctc_keyword_hits(res, kw)
+    nhit = 0
+    for b in range(B):
+        want = O.hyps_of(O.ctc_prefix_beam_search(probs[b], tokenset))
+        assert got[b] == want, b
+        assert hits[b] == O.ctc_keyword_hit(want, kw)
+        nhit += hits[b][0] is not None
+    assert nhit >= B // 2

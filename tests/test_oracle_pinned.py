@@ -160,3 +160,30 @@ def test_oracle_context_expansion_pinned_to_reference_processor():
     for i, (T, D, left, right, skip) in enumerate(g["cases"].tolist()):
         y = O.frame_skip(O.context_expansion(torch.from_numpy(g[f"x{i}"]), left, right), skip)
         assert torch.equal(y, torch.from_numpy(g[f"y{i}"])), i
+
+
+def _ctc_golden_cases():
+    g = golden("ctc")
+    tokenset = set(g["tokenset"].tolist())
+    for i in range(int(g["ncases"])):
+        n = int(g[f"n{i}"])
+        hyps = []
+        for k in range(n):
+            ln = int(g[f"len{i}"][k])
+            hyps.append((tuple(g[f"tok{i}"][k, :ln].tolist()), float(g[f"score{i}"][k]),
+                         [dict(token=int(g[f"tok{i}"][k, j]), frame=int(g[f"frame{i}"][k, j]), prob=float(g[f"prob{i}"][k, j]))
+                          for j in range(ln)]))
+        yield i, torch.from_numpy(g[f"probs{i}"]), (tokenset if bool(g[f"use_set{i}"]) else None), hyps
+
+
+def test_oracle_ctc_prefix_beam_search_pinned_to_reference():
+    """O.ctc_prefix_beam_search == the hypotheses the REFERENCE's wekws/model/loss.py:206-312 returned for the same
+    posteriors (tests/golden/ctc.npz, made by oracle/make_ctc_golden.py): order, prefixes, scores (double, exact),
+    node frames and probabilities; chunked decoding with carried hypotheses == whole utterance."""
+    for i, probs, tokenset, want in _ctc_golden_cases():
+        got = O.hyps_of(O.ctc_prefix_beam_search(probs, tokenset))
+        assert got == want, i
+        cur = None
+        for t0 in range(0, probs.size(0), 17):
+            cur = O.ctc_prefix_beam_search(probs[t0:t0 + 17], tokenset, cur_hyps=cur, frame_offset=t0)
+        assert O.hyps_of(cur) == want, i

@@ -228,13 +228,13 @@ int fsmn_launch(FsmnArgs a, cudaStream_t st) {
   if (a.S > a.B) a.S = a.B;
   a.n_tiles = (a.B + a.S - 1) / a.S;
   const size_t smem = fsmn_smem_bytes(a);
-  WEKWS_REQUIRE(smem <= 227 * 1024, "fsmn: layer widths need %zu bytes of shared memory (max 227 KB)", smem);
-  static bool attr_set[64] = {false};
+  WEKWS_REQUIRE(smem <= 226 * 1024, "fsmn: layer widths need %zu bytes of shared memory (max 226 KB + static)", smem);
+  static size_t attr_bytes[64] = {0};                  // per device: the largest dynamic size opted into so far
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    WEKWS_CUDA_OK(cudaFuncSetAttribute(fsmn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[dev] = true;
+  if (dev >= 0 && dev < 64 && attr_bytes[dev] < smem) {
+    WEKWS_CUDA_OK(cudaFuncSetAttribute(fsmn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes[dev] = smem;
   }
   const int sms = device_sm_count();
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;

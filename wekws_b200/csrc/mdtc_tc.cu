@@ -60,20 +60,9 @@ static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA m
 constexpr int TM_TILE = 160, TM_AHI = 64, TM_ALO = 112, TM_COLS = 512;
 
 __device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-// byte offset of channel ch of frame column col inside X: the 16-byte chunk holding channels 8m..8m+3 sits at chunk
-// (m ^ (col & 7)) of the first 128 bytes, channels 8m+4..8m+7 at the same chunk of the second 128 bytes
-__device__ __forceinline__ uint32_t xoff(int col, int ch) {
-  const uint32_t c = (uint32_t)ch, k = (uint32_t)col;
-  return (k << 8) + ((c & 4u) << 5) + ((((c >> 3) ^ k) & 7u) << 4) + ((c & 3u) << 2);
-}
+// Layout of X: frame column col holds its 64 channels in 256 bytes; the 16-byte chunk with channels 8m..8m+3 sits at
+// chunk (m ^ (col & 7)) of the first 128 bytes, channels 8m+4..8m+7 at the same chunk of the second 128 bytes:
+//   address(col, 8m + 4h + u) = xs + ((col << 8) | ((col & 7) << 4)) ^ (m << 4)  +  128 h  +  4 u
 // 2-D TMA tensor copy global -> shared (box given by the tensor map), completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -312,16 +301,23 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           // (conflict-free in the swizzled layout); 8 lanes write 32 contiguous bytes of one cache row.
           {
             const int off = a.coff[blk];
-            const int npj = pad >= 8 ? pad >> 3 : 1, lgn = 31 - __clz(npj), nitem = nst * 16 * npj;
-            const int jlow = lane & 7, chi = lane >> 3;
+            // lane -> (column j of the slice, channel-quad sub-index): one LDS.128 = 4 channels of one column, then four
+            // stores, each lane-contiguous along a cache row
+            const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
+            const int j = lane & (jpl - 1), qs = lane >> lgj, per = 16 >> (5 - lgj);      // quads passes per stream
+            const int nitem = nst * per;
             for (int it = q; it < nitem; it += 4) {
-              const int jh = it & (npj - 1), r = it >> lgn, cq4 = r & 15, s2 = r >> 4;
-              const int c = 4 * cq4 + chi, jj = 8 * jh + jlow;
-              if (jj < pad) {
-                const int sg2 = grp * spt + s2;
-                const float v = lds_f32(xs + xoff(sg2 * Lw + PADR + T - pad + jj, c));
-                a.out_cache[((size_t)(b0 + sg2) * C + c) * a.P + off + jj] = v;
-              }
+              const int s2 = it / per, cq = (it - s2 * per) * qstep + qs;
+              const int sg2 = grp * spt + s2;
+              const uint32_t cc = (uint32_t)(sg2 * Lw + PADR + T - pad + j);
+              const uint32_t src = ((xs + (cc << 8) + ((cc & 7u) << 4)) ^ ((uint32_t)(cq >> 1) << 4)) + (uint32_t)(cq & 1) * 128u;
+              f32x2 v01, v23;
+              lds_2x2(src, v01, v23);
+              float v0, v1, v2, v3;
+              unpack2(v01, v0, v1);
+              unpack2(v23, v2, v3);
+              float* g = a.out_cache + ((size_t)(b0 + sg2) * C + 4 * cq) * a.P + off + j;
+              g[0] = v0; g[a.P] = v1; g[2 * a.P] = v2; g[3 * a.P] = v3;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_free[grp]);      // the tile's cache columns may be overwritten
@@ -380,16 +376,27 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
                   sts_2x2(ax, pack2(o[0], o[1]), pack2(o[2], o[3]));
                   sts_2x2(ax + 128, pack2(o[4], o[5]), pack2(o[6], o[7]));
                 }
-                if (stack_end) {      // the classifier is linear: W_c (sum of stack outputs) = sum of W_c (stack output)
-                  const float* wc = vec + a.v_wc + (8 * m) * a.odim;
+              }
+            }
+            if (stack_end) {
+              // the classifier is linear: W_c (sum of stack outputs) = sum of W_c (stack output).  A compact loop over
+              // the row just written (own stores, program order) instead of 8 unrolled copies inside the epilogue
+#pragma unroll 1
+              for (int m = 0; m < 8; ++m) {
+                const uint32_t ax = t_own ^ ((uint32_t)m << 4);
+                f32x2 r0, r1, r2, r3;
+                lds_2x2(ax, r0, r1);
+                lds_2x2(ax + 128, r2, r3);
+                float o[8];
+                unpack2(r0, o[0], o[1]); unpack2(r1, o[2], o[3]); unpack2(r2, o[4], o[5]); unpack2(r3, o[6], o[7]);
+                const float* wc = vec + a.v_wc + (8 * m) * a.odim;
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    if (j < a.odim) {
-                      float p = part[j];
+                for (int j = 0; j < 8; ++j) {
+                  if (j < a.odim) {
+                    float p = part[j];
 #pragma unroll
-                      for (int u = 0; u < 8; ++u) p = fmaf(__ldg(wc + u * a.odim + j), o[u], p);
-                      part[j] = p;
-                    }
+                    for (int u = 0; u < 8; ++u) p = fmaf(__ldg(wc + u * a.odim + j), o[u], p);
+                    part[j] = p;
                   }
                 }
               }
@@ -464,7 +471,6 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       const int njobs = a.nblocks * nmine;
       const bool have_cache = a.in_cache != nullptr;
       const int nsl = l == 0 ? 4 : 3, slot0 = l == 0 ? 0 : 4;   // my landing slots: a ring of nsl
-      const int jlow = lane & 7, chi = lane >> 3;
       auto issue_tma = [&](int k) {                    // lane 0; job k = (blk, my m-th stream)
         const int blk = k / nmine, sg = l + 2 * (k - blk * nmine);
         const int pad = a.dil[blk] * (K - 1);
@@ -477,8 +483,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       int k = 0;
       for (int blk = 0; blk < a.nblocks; ++blk) {
         const int pad = a.dil[blk] * (K - 1);
-        const int npj = pad >= 8 ? pad >> 3 : 1, lg = 31 - __clz(npj);
-        const int fx = (pad == 32 ? chi : pad == 16 ? (chi >> 1) : 0) & (npj - 1);   // read-bank spreading
+        // lane -> (column j of the slice, channel-quad sub-index): four loads down the slot's channel rows, one
+        // STS.128 = 4 channels of one column of X
+        const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
+        const int j = lane & (jpl - 1), qs = lane >> lgj;
         for (int i = 0; i < ntile; ++i) {
           // X's pad columns of tile i are free once DW + cache stores (i, blk-1) are done (at blk 0: from the start)
           if (blk > 0) {
@@ -494,12 +502,14 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               const uint32_t use = jobctr + (uint32_t)k, slot = slot0 + use % nsl;
               if (lane == 0) mbar_wait_backoff(&stg_bar[slot], (use / nsl) & 1);
               __syncwarp();
-              const float* src = STG + slot * STG_FLOATS;
+              const float* src = STG + slot * STG_FLOATS + j;
+              const uint32_t col = (uint32_t)(colb + j);
+              const uint32_t tcol = xs + (col << 8) + ((col & 7u) << 4);
 #pragma unroll 4
-              for (int it = 0; it < 16 * npj; ++it) {
-                const int jh = it & (npj - 1), cq4 = it >> lg;
-                const int c = 4 * cq4 + chi, jj = jlow + 8 * (jh ^ fx);
-                if (jj < pad) sts_f32(xs + xoff(colb + jj, c), src[c * pad + jj]);
+              for (int cq = qs; cq < 16; cq += qstep) {
+                const float* s4 = src + 4 * cq * pad;
+                const float a0 = s4[0], a1 = s4[pad], a2 = s4[2 * pad], a3 = s4[3 * pad];
+                sts_2x2((tcol ^ ((uint32_t)(cq >> 1) << 4)) + (uint32_t)(cq & 1) * 128u, pack2(a0, a1), pack2(a2, a3));
               }
             } else {
               const f32x2 z = 0ull;

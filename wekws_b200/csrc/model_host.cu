@@ -514,7 +514,7 @@ int pack_fsmn(wekws_model* m) {
   int m1 = A1 > P ? A1 : P;
   if (A2 > m1) m1 = A2;
   a.sp0 = (int)pad4(m0) + 4; a.sp1 = (int)pad4(m1) + 4; a.spm = (int)pad4(P) + 4;   // +4: rows start in different banks
-  WEKWS_REQUIRE(fsmn_smem_bytes(a) <= 227 * 1024, "fsmn: layer widths (%d, %d, %d) exceed the fused kernel's shared memory", m0, m1, P);
+  WEKWS_REQUIRE(fsmn_smem_bytes(a) <= 226 * 1024, "fsmn: layer widths (%d, %d, %d) exceed the fused kernel's shared memory", m0, m1, P);
   return WEKWS_OK;
 }
 
