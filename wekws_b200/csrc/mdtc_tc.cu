@@ -48,7 +48,7 @@ constexpr int X_BYTES = XCOLS * 256;       // 129024: X[col][64] fp32
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
 constexpr int NSLOT = 7;                   // loader 0: slots 0..3, loader 1: slots 4..6
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
-constexpr int VEC_FLOATS = 512;            // per-block vectors: (K + 3) * 64 floats, K <= 5
+constexpr int VEC_FLOATS = 64;             // per-block vector kept in shared memory: the folded depthwise bias
 constexpr int OFF_X = 0;
 constexpr int OFF_STG = OFF_X + X_BYTES;                   // 129024
 constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 186368 (1024-aligned: SWIZZLE_128B images)
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   __shared__ uint64_t mma_bar[NG], halo_bar[NG], a_rdy[NG], h_free[NG];
   __shared__ uint64_t w_bar[2], w_free[2], vec_bar[2], stg_bar[NSLOT];
+  __shared__ uint64_t dw_tok[NG];                  // depthwise-phase token: passed group -> group (see the conv below)
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   if (tid == 0) {
     for (int i = 0; i < NG; ++i) {
       mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 2); mbar_init(&a_rdy[i], 3); mbar_init(&h_free[i], 4);
+      mbar_init(&dw_tok[i], 4);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&w_bar[i], 1); mbar_init(&w_free[i], NG); mbar_init(&vec_bar[i], 1); }
     for (int i = 0; i < NSLOT; ++i) mbar_init(&stg_bar[i], 1);
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   // phase parities: every waiter keeps its own copy; all copies of a barrier advance in lock step
-  uint32_t mma_par = 0, halo_par = 0, ar_par = 0, vec_par = 0;       // compute / issuer
+  uint32_t mma_par = 0, halo_par = 0, ar_par = 0, vec_par = 0, tok_par = 0;   // compute groups
   uint32_t hf_par = 0;                                               // loaders: bit i = tile i
   uint32_t w_par = 0, wf_par = 0;                                    // bit s = slot s
   uint32_t jobctr = 0;                                               // loader: landing-slot use counter
@@ -259,6 +261,15 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           vec_par ^= 1u << (blk & 1);
           mbar_wait(&halo_bar[grp], halo_par);
           halo_par ^= 1;
+          // The depthwise conv is the shared-memory-bandwidth phase (22 LDS.128 per 8 channels) while the epilogues and
+          // the GEMM waits leave the load/store pipe idle.  Groups that run in lock step all hit it at once and then all
+          // idle; a token handed from group to group (g -> g + 1 -> ... -> 0 of the next block) keeps exactly one
+          // group in this phase, so the others' tensor-core and epilogue phases overlap it.
+          const bool use_tok = ntile > 1 && (a.debug & 1);      // off by default: measured 9 % slower on B200 (profiles/r02_mdtc_notes.md)
+          if (use_tok && !(blk == 0 && grp == 0)) {
+            mbar_wait(&dw_tok[grp], tok_par);
+            tok_par ^= 1;
+          }
           if (q_live) {
             uint32_t tj[5];
 #pragma unroll
@@ -269,21 +280,21 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
               f32x2 acc0, acc1, acc2, acc3;
-              lds_2x2(vb + (uint32_t)(K * C + 8 * m) * 4, acc0, acc1);
-              lds_2x2(vb + (uint32_t)(K * C + 8 * m) * 4 + 16, acc2, acc3);
+              lds_2x2(vb + (uint32_t)(8 * m) * 4, acc0, acc1);          // folded depthwise bias (VEC holds only this now)
+              lds_2x2(vb + (uint32_t)(8 * m) * 4 + 16, acc2, acc3);
 #pragma unroll
               for (int j = 0; j < 5; ++j) {
                 if (KT ? j < KT : j < K) {
                   const uint32_t aj = tj[j] ^ ((uint32_t)m << 4);
-                  f32x2 x0, x1, x2, x3, w0, w1, w2, w3;
+                  f32x2 x0, x1, x2, x3;
                   lds_2x2(aj, x0, x1);
                   lds_2x2(aj + 128, x2, x3);
-                  lds_2x2(vb + (uint32_t)(j * C + 8 * m) * 4, w0, w1);
-                  lds_2x2(vb + (uint32_t)(j * C + 8 * m) * 4 + 16, w2, w3);
-                  acc0 = fma2(w0, x0, acc0);
-                  acc1 = fma2(w1, x1, acc1);
-                  acc2 = fma2(w2, x2, acc2);
-                  acc3 = fma2(w3, x3, acc3);
+                  const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * j + 2 * m]);       // LDCU
+                  const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * j + 2 * m + 1]);
+                  acc0 = fma2(x0, wa.x, acc0);
+                  acc1 = fma2(x1, wa.y, acc1);
+                  acc2 = fma2(x2, wb.x, acc2);
+                  acc3 = fma2(x3, wb.y, acc3);
                 }
               }
               uint32_t h[4], l[4];
@@ -294,6 +305,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               tmem_st4(tm_row + TM_AHI + 4 * m, h);
               tmem_st4(tm_row + TM_ALO + 4 * m, l);
             }
+          }
+          if (use_tok) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dw_tok[grp + 1 == ntile ? 0 : grp + 1]);
           }
           hand_over(0);
           // ---------------- new cache slices of this tile while its pointwise-1 GEMM runs:
@@ -333,9 +348,9 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               uint32_t h[16], l[16];
 #pragma unroll
               for (int mm = 0; mm < 4; ++mm) {
-                f32x2 b0v, b1v, b2v, b3v;
-                lds_2x2(vb + (uint32_t)((K + 1) * C + 32 * half + 8 * mm) * 4, b0v, b1v);
-                lds_2x2(vb + (uint32_t)((K + 1) * C + 32 * half + 8 * mm) * 4 + 16, b2v, b3v);
+                const ulonglong2 ba = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 5 + 8 * half + 2 * mm]);      // b1
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 5 + 8 * half + 2 * mm + 1]);
+                const f32x2 b0v = ba.x, b1v = ba.y, b2v = bb.x, b3v = bb.y;
                 auto E = [&](int u) { return __uint_as_float(dd[8 * mm + u]); };
                 split_pair_rz_relu(add2(pack2(E(0), E(1)), b0v), h[4 * mm + 0], l[4 * mm + 0]);
                 split_pair_rz_relu(add2(pack2(E(2), E(3)), b1v), h[4 * mm + 1], l[4 * mm + 1]);
@@ -359,9 +374,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               for (int mm = 0; mm < 4; ++mm) {
                 const int m = 4 * half + mm;
                 const uint32_t ax = t_own ^ ((uint32_t)m << 4);
-                f32x2 b0v, b1v, b2v, b3v, r0, r1, r2, r3;
-                lds_2x2(vb + (uint32_t)((K + 2) * C + 8 * m) * 4, b0v, b1v);
-                lds_2x2(vb + (uint32_t)((K + 2) * C + 8 * m) * 4 + 16, b2v, b3v);
+                const ulonglong2 ba = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 6 + 2 * m]);                  // b2
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 6 + 2 * m + 1]);
+                const f32x2 b0v = ba.x, b1v = ba.y, b2v = bb.x, b3v = bb.y;
+                f32x2 r0, r1, r2, r3;
                 lds_2x2(ax, r0, r1);
                 lds_2x2(ax + 128, r2, r3);
                 auto E = [&](int u) { return __uint_as_float(dd[8 * mm + u]); };
@@ -406,6 +422,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           group_barrier(grp);                // x' of every row of the tile complete before the next block's conv
         }
 
+        if (ntile > 1 && (a.debug & 1) && grp == 0) {    // the last group's final hand-off: keep the parities in step
+          mbar_wait(&dw_tok[0], tok_par);
+          tok_par ^= 1;
+        }
         // ---- classifier bias + activation: the row's sums are complete in registers
         if (live) {
           float* o = a.out + (size_t)(b0 + sg) * a.out_bstride + (size_t)tt * a.odim;
@@ -438,9 +458,9 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
           bulk_g2s(Wslot[slot], src, W_SLOT, &w_bar[slot]);
         };
-        auto load_vec = [&](int blk) {               // taps + biases of block blk -> VEC[blk & 1]
-          mbar_arrive_expect_tx(&vec_bar[blk & 1], (uint32_t)(a.v_blk_stride * 4));
-          bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, vec + a.v_blocks + blk * a.v_blk_stride, (uint32_t)(a.v_blk_stride * 4),
+        auto load_vec = [&](int blk) {               // folded depthwise bias of block blk -> VEC[blk & 1]
+          mbar_arrive_expect_tx(&vec_bar[blk & 1], (uint32_t)(C * 4));
+          bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, vec + a.v_blocks + blk * a.v_blk_stride + K * C, (uint32_t)(C * 4),
                    &vec_bar[blk & 1]);
         };
         auto wait_free = [&](int slot) {             // every tile's MMAs on the slot's current weights are done
@@ -541,6 +561,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
 
 bool tc_eligible(const TcArgs& a, int padmax) {
   if (a.idim % 8 != 0 || a.idim > 96 || a.odim > 8 || a.ktaps > 5) return false;   // A operand: 48 TMEM columns = K 96
+  if (a.nblocks > kTcMaxBlocks) return false;                                        // taps / biases travel in the parameter block
   if (padmax > 32 || a.P % 4 != 0) return false;
   for (int b = 0; b < a.nblocks; ++b)
   {
@@ -580,7 +601,10 @@ int mdtc_tc_launch(TcArgs a, int padmax, cudaStream_t st) {
   int smax = NG * a.spt;                               // streams resident per pass
   if (smax > XCOLS / Lw) smax = XCOLS / Lw;
   a.smax = smax;
-  a.debug = 0;
+  {
+    const char* dbg = getenv("WEKWS_TC_DEBUG");     // bit 0: depthwise-phase token on (A/B timing; results unchanged)
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   // tensor maps over the incoming cache (B*64 rows of P floats): one per distinct slice width
   if (a.in_cache != nullptr) {
     EncodeTiledFn enc = encode_tiled_fn();

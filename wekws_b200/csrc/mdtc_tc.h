@@ -8,6 +8,8 @@
 
 namespace wekws {
 
+constexpr int kTcMaxBlocks = 17;   // 17 x 7 x 256 B = 30464 B of the 32764-byte parameter block (mdtc: 1 + 4 x 4)
+
 struct TcArgs {
   const float* feats;      // (B, T, idim), stream stride feat_bstride
   const float* in_cache;   // (B, 64, P) or nullptr
@@ -26,7 +28,13 @@ struct TcArgs {
   int smax, spt, padr;     // streams per pass / per tile, roundup4(max pad) (set by mdtc_tc_launch)
   int tmap_idx[kMaxBlocks];               // block -> tensor map (one per distinct pad)
   alignas(64) CUtensorMap tmap[4];        // 2-D maps over in_cache viewed as [B*64][P], box [64][pad]
+  // Per-block depthwise taps and the two GEMM biases, passed BY VALUE in the kernel parameter block (constant bank):
+  // the kernel reads them with uniform loads (LDCU) straight into uniform registers that FFMA2 / FADD2 take as
+  // operands, so 1792 of the 3840 shared-memory bytes a frame used to pull per block (the same 16 bytes fetched by
+  // every lane) never touch the load/store pipe.  [blk][0..4] = taps (zero beyond ktaps), [5] = b1, [6] = b2; 64 each.
+  alignas(16) float4 cw[kTcMaxBlocks][7 * 16];
 };
+static_assert(sizeof(TcArgs) <= 32764, "kernel parameter block exceeds 32764 bytes");
 
 bool tc_eligible(const TcArgs& a, int padmax);
 int tc_max_T();

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "conv_backbone.h"
 #include "gru.h"
+#include "gru_tc.h"
 #include "mdtc_tc.h"
 #include "tcn_tc.h"
 #include "dstcn_tc.h"
@@ -101,6 +102,8 @@ struct wekws_model {
   bool ds_ok = false;                       // tensor-core path for the depthwise-separable TCN (hidden 256)
   DsTcArgs dsargs{};
   FsmnArgs fsmn{};                          // FSMN backbone (fsmn.cu): weights live in h_vec / d_vec
+  bool gru_tc_ok = false;                   // cluster / tensor-core GRU (gru_tc.cu): images live in h_wimg / d_wimg
+  GruTcArgs grutc{};
 };
 
 namespace {
@@ -295,6 +298,17 @@ void pack_tc(wekws_model* m) {
   if (a.idim > 64) write_w_image(m->h_wimg.data() + 16384, m->folded[0], a.idim, 64);
   for (int g = 0; g < 2 * a.nblocks; ++g)
     write_w_image(m->h_wimg.data() + (size_t)(2 + g) * 16384, m->folded[1 + g], 64, 0);
+  // depthwise taps + the two GEMM biases of every block, passed by value with the launch (mdtc_tc.h TcArgs::cw)
+  for (int b = 0; b < a.nblocks; ++b) {
+    const float* vb = m->h_vec.data() + a.v_blocks + (size_t)b * a.v_blk_stride;
+    float* dst = reinterpret_cast<float*>(&t.cw[b][0]);
+    for (int j = 0; j < 5; ++j)
+      for (int ch = 0; ch < 64; ++ch) dst[j * 64 + ch] = j < a.ktaps ? vb[j * 64 + ch] : 0.f;
+    for (int ch = 0; ch < 64; ++ch) {
+      dst[5 * 64 + ch] = vb[(a.ktaps + 1) * 64 + ch];
+      dst[6 * 64 + ch] = vb[(a.ktaps + 2) * 64 + ch];
+    }
+  }
   m->tc_ok = true;
 }
 
@@ -436,6 +450,26 @@ int pack_gru(wekws_model* m) {
   }
   if ((rc = pack_classifier(m, H, &a.v_wc, &a.v_bc))) return rc;
   a.L = L; a.H = H; a.idim = idim; a.odim = c.odim; a.act = c.activation; a.has_cmvn = m->has_cmvn ? 1 : 0;
+  // cluster / tensor-core variant: per-rank operand images of the hidden-unit slices
+  m->gru_tc_ok = false;
+  m->h_wimg.clear();
+  if (gru_tc_eligible(L, H, idim)) {
+    const float* wih[4];
+    const float* whh[4];
+    for (int l = 0; l < L; ++l) {
+      const std::string sfx = "_l" + std::to_string(l);
+      if ((rc = get_tensor(m, "backbone.weight_ih" + sfx, (size_t)G * H, &wih[l]))) return rc;
+      if ((rc = get_tensor(m, "backbone.weight_hh" + sfx, (size_t)G * H, &whh[l]))) return rc;
+    }
+    m->h_wimg.assign(gru_tc_image_bytes(), 0);
+    gru_tc_pack(m->h_wimg.data(), wp, idim, wih, whh, L, bf16_rn, bf16_to_f);
+    GruTcArgs& t = m->grutc;
+    memset(&t, 0, sizeof(t));
+    t.L = L; t.idim = idim; t.odim = c.odim; t.act = c.activation; t.has_cmvn = a.has_cmvn;
+    t.v_mean = a.v_mean; t.v_istd = a.v_istd; t.v_bp = a.v_bp; t.v_layers = a.v_layers;
+    t.v_layer_stride = a.v_layer_stride; t.v_wc = a.v_wc; t.v_bc = a.v_bc;
+    m->gru_tc_ok = true;
+  }
   return WEKWS_OK;
 }
 
@@ -606,6 +640,11 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
     WEKWS_REQUIRE(m->conv_max_T >= 1, "model does not fit the fused kernel's shared memory");
   } else {
     m->gru.vec = m->d_vec;
+    if (m->gru_tc_ok) {
+      WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_wimg, m->h_wimg.size()));
+      WEKWS_CUDA_OK(cudaMemcpy(m->d_wimg, m->h_wimg.data(), m->h_wimg.size(), cudaMemcpyHostToDevice));
+      m->grutc.vec = m->d_vec; m->grutc.wimg = m->d_wimg;
+    }
   }
   m->finalized = true;
   return WEKWS_OK;
@@ -618,6 +657,7 @@ extern "C" int wekws_model_set_precision(wekws_model* m, int mode) {
 }
 
 extern "C" int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T) {
+  if (m && m->finalized && m->gru_tc_ok && m->precision == 0 && T >= 1) return 1;
   return (m && m->finalized && (m->tc_ok || m->tcn_ok || m->ds_ok) && m->precision == 0 && T >= 8) ? 1 : 0;
 }
 
@@ -670,6 +710,12 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
       int rc = fsmn_launch(a, st);
       if (rc) return rc;
     }
+  } else if (m->cfg.backbone == WEKWS_BACKBONE_GRU && m->gru_tc_ok && m->precision == 0) {
+    GruTcArgs a = m->grutc;
+    a.feats = d_feats; a.in_cache = d_in_cache; a.out = d_out; a.out_cache = d_out_cache;
+    a.B = (int)B; a.T = (int)T;
+    int rc = gru_tc_launch(a, st);
+    if (rc) return rc;
   } else if (m->cfg.backbone == WEKWS_BACKBONE_GRU) {
     GruArgs a = m->gru;
     a.feats = d_feats; a.in_cache = d_in_cache; a.out = d_out; a.out_cache = d_out_cache;
