@@ -310,8 +310,9 @@ class Runner:
         cshape = (2, B, 128) if gru else (B, model.hdim, model.backbone.padding)
         pcm_mode = workload.startswith("pcm_")
         if pcm_mode:
-            from wekws_b200 import Fbank
+            from wekws_b200 import Fbank, Pipeline
             fb = Fbank(idim)
+            pipe = Pipeline(fb, model)
             pcm = [synth.pcm_int16(B, PCM_SAMPLES, seed=1234 + rank * 17 + s).to(dev) for s in range(NSETS)]
             feat_buf = torch.empty(B, T, idim, device=dev)
             feats = [feat_buf] * NSETS
@@ -323,7 +324,7 @@ class Runner:
         def step(i):
             s = i % NSETS
             if pcm_mode:
-                model(fb(pcm[s], out=feat_buf))
+                pipe(pcm[s])
             else:
                 _, caches[s] = model(feats[s], caches[s])
 
@@ -387,7 +388,7 @@ class Runner:
                         in_ready[nb].record(copy_stream)
                 main_stream.wait_event(in_ready[b])
                 if pcm_mode:
-                    y, _ = model(fb(d_in[b], out=feat_buf))
+                    y, _ = pipe(d_in[b])
                 else:
                     y, caches[s] = model(d_in[b], caches[s])
                 in_free[b].record(main_stream)
@@ -431,7 +432,7 @@ class Runner:
                 a.record()
                 d_in[0].copy_(h_in[i % NSETS], non_blocking=True)
                 if pcm_mode:
-                    y, _ = model(fb(d_in[0], out=feat_buf))
+                    y, _ = pipe(d_in[0])
                 else:
                     y, caches[0] = model(d_in[0], caches[0])
                 h_out[0].copy_(y, non_blocking=True)
@@ -493,7 +494,7 @@ class Runner:
                     "h2d_bytes_per_step": (B * PCM_SAMPLES * 2) if pcm_mode else (B * T * idim * 4),
                     "d2h_bytes_per_step": B * T * model.odim * 4, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "batch_latency": e2e_lat,
-                    "api": "wekws_b200.KWSModel.forward(feats, cache)" + (" after wekws_b200.Fbank(pcm)" if pcm_mode else "")
+                    "api": ("wekws_b200.Pipeline(Fbank, KWSModel)(pcm) -> wekws_pipeline_forward" if pcm_mode else "wekws_b200.KWSModel.forward(feats, cache)")
                            + "; pinned host input in, posteriors out, H2D double-buffered on a copy stream; "
                              "own step count: warm-up until stable (>= 0.5 s), then >= 1 s timed"},
             "gpu_launches": launches, "tensor_cores": tc,

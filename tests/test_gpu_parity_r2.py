@@ -393,3 +393,24 @@ def test_gru_cluster_tensor_core_path(B, T):
         yt, hd = m(x[:, t:t + 1].to(DEV), hd)
         ys.append(yt)
     assert float((torch.cat(ys, 1) - ytc).abs().max()) <= 2e-5 and float((hd - htc).abs().max()) <= 2e-5
+
+
+def test_pipeline_native_call_matches_two_step_chain_and_oracle():
+    """Pipeline(frontend, model)(pcm) == model(frontend(pcm)) bit for bit (same kernels, L2-pinned features), for Fbank
+    and MFCC front-ends, with a carried cache, and against the oracle at the posterior gate."""
+    from wekws_b200 import Pipeline
+    cfg, m, sd = _model("mdtc", cmvn=True)
+    pcm = synth.pcm_int16(33, 16000, seed=4)
+    for fe in (Fbank(80), Mfcc(80, 80)):
+        pipe = Pipeline(fe, m)
+        y1, c1 = pipe(pcm.to(DEV))
+        y2, c2 = m(fe(pcm.to(DEV)))
+        assert torch.equal(y1, y2) and torch.equal(c1, c2)
+        y3, c3 = pipe(pcm.to(DEV), c1)
+        y4, c4 = m(fe(pcm.to(DEV)), c2)
+        assert torch.equal(y3, y4) and torch.equal(c3, c4)
+    ref_f = torch.stack([O.mfcc(pcm[b].float(), 80, 80) for b in range(pcm.shape[0])])
+    y_ref, _ = O.kws_forward(sd, cfg, ref_f, None)
+    assert float((y1.cpu() - y_ref).abs().max()) <= TOL_POST
+    with pytest.raises(ValueError):
+        Pipeline(Fbank(40), m)

@@ -5,6 +5,7 @@ Public surface mirrors the reference (wenet-e2e/wekws):
     Fbank, fbank             <- torchaudio.compliance.kaldi.fbank as the reference calls it
     Mfcc, mfcc               <- torchaudio.compliance.kaldi.mfcc  (processor.py:157-166, the mdtc configs' front-end)
     load_cmvn, load_kaldi_cmvn <- wekws/utils/cmvn.py
+    Pipeline(frontend, model) <- raw PCM -> posteriors in one native call (stream_kws_ctc.py:482-487 composition)
     patch_reference()        -> makes `wekws.model.kws_model` resolve to this implementation
     det_stats, det_curve     <- wekws/bin/compute_det.py threshold sweep (on the device, bit-exact)
     ctc_prefix_beam_search, ctc_keyword_hits, write_ctc_scores <- wekws/model/loss.py:206-312 + score_ctc.py:198-226
@@ -18,9 +19,10 @@ from .kws_model import GlobalCMVN, KWSModel, init_model
 from .ctc import ctc_keyword_hits, ctc_prefix_beam_search, ctc_state, write_ctc_scores
 from .export import export_native
 from .overlay import patch_reference
+from .pipeline import Pipeline
 from .postproc import context_expansion, det_curve, det_stats, det_thresholds
 
 __all__ = ["init_model", "KWSModel", "GlobalCMVN", "Fbank", "fbank", "Mfcc", "mfcc", "load_cmvn", "load_kaldi_cmvn",
            "model_config", "MODEL_NAMES", "patch_reference", "export_native", "det_stats", "det_curve", "det_thresholds", "context_expansion",
-           "ctc_prefix_beam_search", "ctc_keyword_hits", "ctc_state", "write_ctc_scores"]
+           "Pipeline", "ctc_prefix_beam_search", "ctc_keyword_hits", "ctc_state", "write_ctc_scores"]
 __version__ = "0.1.0"

@@ -424,6 +424,16 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
       // ---- classifier + activation on x (tcn.py:165 -> classifier.py:63-67); partial sums reuse the coefficient area
       wd_mark(40000);
       const int odim = a.odim;
+      if (a.hidden != nullptr) {
+        // wide classifier heads run as their own tcgen05 GEMM (linear_tc.cu): hand over x as (stream, frame, 256) rows.
+        // lanes = consecutive rows (conflict-free reads of X[c][row]); each warp walks the channels
+        for (int c = warp; c < C; c += NCW) {
+          for (int r = lane; r < rows; r += 32) {
+            const int tt = r / ns, ss = r - tt * ns;
+            a.hidden[(size_t)(b0 + ss) * a.hidden_bstride + (size_t)tt * C + c] = X[c * RPX + r];
+          }
+        }
+      } else {
       {
         const int r = tid & 127, part = tid >> 7;
         if (r < rows) {
@@ -445,6 +455,7 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
         a.out[(size_t)(b0 + ss) * a.out_bstride + (size_t)tt * odim + j] = y;
       }
     }
+      }
     __syncthreads();       // pass boundary
   }
 
@@ -456,7 +467,7 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
 }  // namespace
 
 bool dstcn_tc_eligible(const DsTcArgs& a, int hdim) {
-  return hdim == C && a.ktaps == KT && a.idim % 8 == 0 && a.idim >= 8 && a.idim <= 128 && a.odim >= 1 && a.odim <= 4 &&
+  return hdim == C && a.ktaps == KT && a.idim % 8 == 0 && a.idim >= 8 && a.idim <= 128 && a.odim >= 1 && (a.odim <= 4 || a.hidden != nullptr) &&
          a.v_blocks % 4 == 0 && a.v_blk_stride % 4 == 0;
 }
 

@@ -24,6 +24,8 @@ struct DsTcArgs {
   int coff[kMaxBlocks];
   int spt;                 // streams per 128-row tile (set by dstcn_tc_launch)
   int aliased;             // out_cache overlaps in_cache (set by dstcn_tc_launch)
+  float* hidden;           // non-null: skip the classifier and write the final x as (B, T, 256) rows (stream stride
+  long long hidden_bstride;  // hidden_bstride) for the tensor-core classifier (linear_tc.cu) that follows
   int prefetch_ok;         // in_cache present and 16-byte aligned with 16-byte stream pitch (set by dstcn_tc_launch)
 };
 

@@ -9,7 +9,7 @@
 // bf16 x3 split, fp32 accumulate in TMEM), and hands the new h values to its 7 peers through distributed shared
 // memory -- each value is split into bf16 hi/lo once, by its producer, and stored straight into the K-major
 // SWIZZLE_128B operand image every CTA's next GEMM reads.  Per step and CTA: 99 MMAs, 96 remote 16-byte stores per
-// stream row, five cluster barriers; no weight byte moves after the prologue.
+// stream row, three cluster barriers; no weight byte moves after the prologue.
 //
 // Roles (128 threads): warps 0-1 own the 64 stream rows (TMEM lanes 0..63): feature split, gate math, exchanges,
 // classifier; warp 2 lane 0 issues the MMAs; warp 3 loads the weight images (bulk async copies) in the prologue.
@@ -44,7 +44,8 @@ constexpr int OFF_END = OFF_HOWN + 2 * M * UPC * 4;
 constexpr int SMEM_BYTES = OFF_END + 1024;
 static_assert(OFF_WP % 1024 == 0 && OFF_W % 1024 == 0 && W_SLABB % 1024 == 0, "operand images must be 1024-byte aligned");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
-// TMEM columns: feature operand hi [0,48) lo [48,96); accumulators D_lin [96,112), D1 [112,160), D2 [160,208)
+// TMEM columns: feature operand hi [0,48) lo [48,96); accumulators D_lin [96,112), D1 = x W_ih^T [112,160),
+// D2 = h W_hh^T of layer l at [160 + 48 l, +48)
 constexpr int TM_FHI = 0, TM_FLO = 48, TM_DLIN = 96, TM_D1 = 112, TM_D2 = 160, TM_COLS = 256;
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -87,10 +88,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  // zero the guard slab and this CTA's images once (phantom rows / unused K columns must stay finite is NOT required,
-  // but never-written rows of real images would otherwise hold NaN patterns that poison nothing -- rows are independent)
-  for (int i = tid; i < (OFF_WP - OFF_AX) / 16; i += NT) reinterpret_cast<uint4*>(base + OFF_AX)[i] = make_uint4(0, 0, 0, 0);
-
+  // (no zero fill: rows past the tile's streams and the phantom rows 64..127 of the M = 128 MMAs only ever feed
+  // accumulator rows nobody reads -- GEMM rows are independent)
   // ---- prologue: this rank's weight images -> shared memory (stay for the whole launch)
   if (warp == 3 && lane == 0) {
     const uint32_t bytes = 4 * WP_SLAB + (uint32_t)L * W_LAYER;
@@ -145,24 +144,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
     const int m = tid;                     // my stream row (row owners)
     const bool live = row_owner && m < Mv;
     float* hown = reinterpret_cast<float*>(base + OFF_HOWN);
-    // ---- initial hidden state: every CTA splits the whole tile's h into its own images; its own units also in fp32
-    if (row_owner) {
+    // ---- initial hidden state: every CTA splits the whole tile's h into its own images; its own units also in fp32.
+    // All 128 threads: thread -> (row tid & 63, half tid >> 6 of the 128 units); the 16 float4 loads of a layer are
+    // issued together (one memory latency per layer instead of one per 8 values)
+    {
+      const int hr = tid & (M - 1), half = tid >> 6;
+      const bool hlive = hr < Mv;
       for (int l = 0; l < L; ++l) {
-        const float* src = (a.in_cache != nullptr && live) ? a.in_cache + ((size_t)l * a.B + b0 + m) * H : nullptr;
-        uint8_t* img = base + OFF_AH + l * 4 * SLAB;
-        for (int k0 = 0; k0 < H; k0 += 8) {
-          float v[8];
+        float4 v4[16];
+        const float4* src = (a.in_cache != nullptr && hlive)
+                                ? reinterpret_cast<const float4*>(a.in_cache + ((size_t)l * a.B + b0 + hr) * H + 64 * half) : nullptr;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = src ? __ldg(src + k0 + u) : 0.f;
+        for (int i = 0; i < 16; ++i) v4[i] = src ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint8_t* img = base + OFF_AH + l * 4 * SLAB;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                 // 8 chunks of 8 units
+          const float4 p0 = v4[2 * c], p1 = v4[2 * c + 1];
           uint4 hi, lo;
-          split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
-          split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
-          const uint32_t off = a_off(m, k0);
+          split2(p0.x, p0.y, hi.x, lo.x); split2(p0.z, p0.w, hi.y, lo.y);
+          split2(p1.x, p1.y, hi.z, lo.z); split2(p1.z, p1.w, hi.w, lo.w);
+          const int k0 = 64 * half + 8 * c;
+          const uint32_t off = a_off(hr, k0);
           *reinterpret_cast<uint4*>(img + off) = hi;
           *reinterpret_cast<uint4*>(img + off + SLAB) = lo;
           if ((k0 >> 4) == (int)rank) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) hown[(l * M + m) * UPC + (k0 & 15) + u] = v[u];
+            float* ho = hown + (l * M + hr) * UPC + (k0 & 15);
+            *reinterpret_cast<float4*>(ho) = p0;
+            *reinterpret_cast<float4*>(ho + 4) = p1;
           }
         }
       }
@@ -173,30 +181,45 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
       // ================= preprocessing Linear + ReLU for my 16 output units            (subsampling.py:53-57)
       if (row_owner) {
         const float* src0 = a.feats + ((size_t)(b0 + m) * T + t) * a.idim;
-        for (int ch = 0; ch < 2 * ksf; ++ch) {
-          float v[8];
+        // the whole feature row in flight at once (idim <= 96: 24 float4), then CMVN + split chunk by chunk
+        float4 f4[24];
+        const bool vec4 = (a.idim & 3) == 0 && (reinterpret_cast<uintptr_t>(src0) & 15) == 0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = 0.f;
-          const int k0 = 8 * ch;
-          if (live && k0 < a.idim) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (k0 + u < a.idim) {
-                float x = __ldg(src0 + k0 + u);
-                if (a.has_cmvn) x = (x - __ldg(vec + a.v_mean + k0 + u)) * __ldg(vec + a.v_istd + k0 + u);
-                v[u] = x;
-              }
+        for (int i = 0; i < 24; ++i) {
+          f4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && 4 * i < a.idim) {
+            if (vec4) f4[i] = __ldg(reinterpret_cast<const float4*>(src0) + i);
+            else {
+              f4[i].x = __ldg(src0 + 4 * i);
+              if (4 * i + 1 < a.idim) f4[i].y = __ldg(src0 + 4 * i + 1);
+              if (4 * i + 2 < a.idim) f4[i].z = __ldg(src0 + 4 * i + 2);
+              if (4 * i + 3 < a.idim) f4[i].w = __ldg(src0 + 4 * i + 3);
             }
           }
-          uint32_t h4[4], l4[4];
-          split2(v[0], v[1], h4[0], l4[0]); split2(v[2], v[3], h4[1], l4[1]);
-          split2(v[4], v[5], h4[2], l4[2]); split2(v[6], v[7], h4[3], l4[3]);
-          const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
-          tmem_st4(trow + TM_FHI + 4 * ch, h4);
-          tmem_st4(trow + TM_FLO + 4 * ch, l4);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 12; ++ch) {
+          if (ch < 2 * ksf) {
+            float v[8] = {f4[2 * ch].x, f4[2 * ch].y, f4[2 * ch].z, f4[2 * ch].w,
+                          f4[2 * ch + 1].x, f4[2 * ch + 1].y, f4[2 * ch + 1].z, f4[2 * ch + 1].w};
+            const int k0 = 8 * ch;
+            if (a.has_cmvn && live) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (k0 + u < a.idim) v[u] = (v[u] - __ldg(vec + a.v_mean + k0 + u)) * __ldg(vec + a.v_istd + k0 + u);
+            }
+            uint32_t h4[4], l4[4];
+            split2(v[0], v[1], h4[0], l4[0]); split2(v[2], v[3], h4[1], l4[1]);
+            split2(v[4], v[5], h4[2], l4[2]); split2(v[6], v[7], h4[3], l4[3]);
+            const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+            tmem_st4(trow + TM_FHI + 4 * ch, h4);
+            tmem_st4(trow + TM_FLO + 4 * ch, l4);
+          }
         }
         tmem_st_wait();
       }
+      // One issue for everything that does not depend on this step's exchanges: the Linear and the h-parts gh = h W_hh^T
+      // of BOTH layers (they read the previous step's h images), so only the x-parts sit on the critical path later
       issue([&]() {
         const uint32_t d = tmem + TM_DLIN;
         uint32_t acc = 0;
@@ -207,6 +230,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
           for (int k = 0; k < ks; ++k) umma_bf16_ts(d, tmem + TM_FLO + 32 * s + 8 * k, whi + 2 * k, idesc16, 1);
           for (int k = 0; k < ks; ++k) umma_bf16_ts(d, tmem + TM_FHI + 32 * s + 8 * k, wlo + 2 * k, idesc16, 1);
         }
+        for (int l = 0; l < L; ++l)
+          gemm_ss(tmem + TM_D2 + NG * l, sbase + OFF_AH + l * 4 * SLAB, sbase + OFF_W + l * W_LAYER + 4 * W_SLABB, W_SLABB, 2, idesc48);
       });
       // x0 of my units -> every CTA's X0 image (the previous step's layer-0 GEMMs are long done: five barriers ago)
       if (row_owner) {
@@ -227,17 +252,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
           st_cluster_v4(r0 + SLAB, lo[0], lo[1], lo[2], lo[3]); st_cluster_v4(r1 + SLAB, lo[4], lo[5], lo[6], lo[7]);
         }
       }
-      cluster_barrier();                   // X0 complete in every CTA
+      tc_fence_before();
+      cluster_barrier();                   // X0 complete in every CTA; every CTA's h-part GEMMs have read the old h images
 
       // ================= GRU layers
       for (int l = 0; l < L; ++l) {
         const uint32_t x_img = l == 0 ? sbase + OFF_AX : sbase + OFF_AH + (l - 1) * 4 * SLAB;
         const uint32_t h_img = sbase + OFF_AH + l * 4 * SLAB;
         const uint32_t w_l = sbase + OFF_W + l * W_LAYER;
-        issue([&]() {
-          gemm_ss(tmem + TM_D1, x_img, w_l, W_SLABB, 2, idesc48);                    // gi = x W_ih^T (my 48 gate rows)
-          gemm_ss(tmem + TM_D2, h_img, w_l + 4 * W_SLABB, W_SLABB, 2, idesc48);      // gh = h W_hh^T
-        });
+        issue([&]() { gemm_ss(tmem + TM_D1, x_img, w_l, W_SLABB, 2, idesc48); });       // gi = x W_ih^T (my 48 gate rows)
         uint32_t hi[8], lo[8];
         if (row_owner) {
           const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
@@ -248,20 +271,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
           const float* bih = vec + a.v_layers + (size_t)l * a.v_layer_stride + 2 * H * 3 * H;   // b_ih (384) then b_hh (384)
           const float* bhh = bih + 3 * H;
           float rg[16];
-          tmem_ld16(trow + TM_D2, gh);                                                  // r gate
+          const uint32_t td2 = trow + TM_D2 + NG * l;
+          tmem_ld16(td2, gh);                                                           // r gate
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int j = UPC * rank + u;
             rg[u] = sigmoidf_acc(gi[u] + __ldg(bih + j) + gh[u] + __ldg(bhh + j));
           }
           float zg[16];
-          tmem_ld16(trow + TM_D2 + 16, gh);                                             // z gate
+          tmem_ld16(td2 + 16, gh);                                                      // z gate
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int j = H + UPC * rank + u;
             zg[u] = sigmoidf_acc(gi[16 + u] + __ldg(bih + j) + gh[u] + __ldg(bhh + j));
           }
-          tmem_ld16(trow + TM_D2 + 32, gh);                                             // n gate
+          tmem_ld16(td2 + 32, gh);                                                      // n gate
           float* ho = hown + (l * M + m) * UPC;
           float hn[16];
 #pragma unroll
@@ -274,8 +298,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
 #pragma unroll
           for (int u = 0; u < 8; ++u) split2(hn[2 * u], hn[2 * u + 1], hi[u], lo[u]);
         }
-        tc_fence_before();
-        cluster_barrier();                 // every CTA's GEMMs have read the old h image: it may be overwritten
+        // (the old h image was last read by the h-part GEMMs issued at the top of the step, which every CTA finished
+        // before the X0 barrier; layer 1's x-part reads the NEW h0 image, after the barrier below)
         if (row_owner) {
           const uint32_t o0 = h_img + a_off(m, UPC * rank), o1 = h_img + a_off(m, UPC * rank + 8);
 #pragma unroll
@@ -285,6 +309,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
             st_cluster_v4(r0 + SLAB, lo[0], lo[1], lo[2], lo[3]); st_cluster_v4(r1 + SLAB, lo[4], lo[5], lo[6], lo[7]);
           }
         }
+        tc_fence_before();
         cluster_barrier();                 // the new h of all 128 units is in every CTA's image
       }
 

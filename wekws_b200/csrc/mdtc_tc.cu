@@ -38,15 +38,17 @@ namespace {
 using namespace tc;
 
 constexpr int NG = 3;                      // row tiles in flight == compute groups
-constexpr int NCW = 4 * NG;                // compute warps
-constexpr int W_WGT = NCW;                 // warp 12: weight / vector ring
-constexpr int W_LD = W_WGT + 1;            // warps 13, 14: cache loaders
-constexpr int NT_TC = (W_LD + 2) * 32;     // 480 threads: <= 4 warps per scheduler -> 128 registers per thread
+constexpr int NCG = 2;                     // threads per row: thread (q, g) owns channels [32 g, 32 g + 32) of row 32 q + lane
+constexpr int WPG = 4 * NCG;               // warps per group (tile)
+constexpr int NCW = NG * WPG;              // compute warps (24)
+constexpr int W_WGT = NCW;                 // warp 24: weight / vector ring
+constexpr int W_LD = W_WGT + 1;            // warps 25..27: cache loaders, one per tile
+constexpr int NT_TC = (W_LD + NG) * 32;    // 896 threads: 7 warps per scheduler -> 72 registers per thread
 constexpr int C = 64;
 constexpr int XCOLS = 504;                 // frame columns of X (n_streams * Lw <= XCOLS)
 constexpr int X_BYTES = XCOLS * 256;       // 129024: X[col][64] fp32
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
-constexpr int NSLOT = 7;                   // loader 0: slots 0..3, loader 1: slots 4..6
+constexpr int NSLOT = 7;                   // TMA landing slots, shared out among the tiles' loaders by stream count
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
 constexpr int VEC_FLOATS = 64;             // per-block vector kept in shared memory: the folded depthwise bias
 constexpr int OFF_X = 0;
@@ -59,7 +61,7 @@ static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA m
 // TMEM columns of tile i: [160 i, 160 i + 64) accumulator, + 64.. A hi (<= 48 cols = K 96), + 112.. A lo
 constexpr int TM_TILE = 160, TM_AHI = 64, TM_ALO = 112, TM_COLS = 512;
 
-__device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+__device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(32 * WPG) : "memory"); }
 // Layout of X: frame column col holds its 64 channels in 256 bytes; the 16-byte chunk with channels 8m..8m+3 sits at
 // chunk (m ^ (col & 7)) of the first 128 bytes, channels 8m+4..8m+7 at the same chunk of the second 128 bytes:
 //   address(col, 8m + 4h + u) = xs + ((col << 8) | ((col & 7) << 4)) ^ (m << 4)  +  128 h  +  4 u
@@ -68,6 +70,128 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
+}
+
+
+// The service roles are separate NON-INLINED functions on purpose: compiled on their own they do not compete with the
+// compute groups for uniform registers, which is what lets ptxas keep the per-block tap / bias constants of the
+// compute code in the uniform datapath (LDCU + FFMA2 / FADD2 with UR operands) instead of vector LDC loads.
+struct Bars {
+  uint64_t *mma_bar, *halo_bar, *a_rdy, *h_free, *w_bar, *w_free, *vec_bar, *stg_bar;
+};
+
+// WEIGHT / VECTOR RING (one thread): slot 0 carries Linear atom 0, W1(0), W1(1), ...; slot 1 [Linear atom 1], W2(0), ...
+__device__ __noinline__ void weights_role(const TcArgs& a, uint8_t* base, Bars B, int K, int natoms, uint32_t& wf_par) {
+  uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
+  float* VEC = reinterpret_cast<float*>(base + OFF_VEC);
+  auto load_w = [&](int slot, const uint8_t* src) {
+    mbar_arrive_expect_tx(&B.w_bar[slot], W_SLOT);
+    bulk_g2s(Wslot[slot], src, W_SLOT, &B.w_bar[slot]);
+  };
+  auto load_vec = [&](int blk) {               // folded depthwise bias of block blk -> VEC[blk & 1]
+    mbar_arrive_expect_tx(&B.vec_bar[blk & 1], (uint32_t)(C * 4));
+    bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, a.vec + a.v_blocks + blk * a.v_blk_stride + K * C, (uint32_t)(C * 4),
+             &B.vec_bar[blk & 1]);
+  };
+  auto wait_free = [&](int slot) {             // every tile's MMAs on the slot's current weights are done
+    mbar_wait_backoff(&B.w_free[slot], (wf_par >> slot) & 1);
+    wf_par ^= 1u << slot;
+  };
+  load_vec(0);
+  if (a.nblocks > 1) load_vec(1);
+  load_w(0, a.wimg);
+  if (natoms > 1) load_w(1, a.wimg + W_SLOT);
+  for (int b = 0; b <= a.nblocks; ++b) {
+    const uint8_t* wb = a.wimg + (size_t)(2 + 2 * b) * W_SLOT;
+    wait_free(0);
+    if (b < a.nblocks) load_w(0, wb);
+    // every tile has handed over DW(b-1), hence finished block b-2: VEC[b & 1] is free
+    if (b >= 2 && b < a.nblocks) load_vec(b);
+    if (b > 0 || natoms > 1) wait_free(1);
+    if (b < a.nblocks) load_w(1, wb + W_SLOT);
+  }
+}
+
+// LOADER WARP i serves tile i only: per (block, stream of the tile) one 2-D TMA copy [64][pad] into a landing slot,
+// then the warp transposes it into the pad columns in front of the stream's frames in X.  A dedicated loader per tile
+// means a group never queues behind another tile's slices (the round-2 profile showed the groups waiting 14 % of the
+// time on halo_bar with two loaders walking the tiles in order).  The tile's ring of `nsl` landing slots is refilled
+// the moment a slot is drained, i.e. the copy for the same stream of the NEXT block is in flight a whole block ahead.
+__device__ __noinline__ void loader_role(const TcArgs& a, uint8_t* base, Bars B, int i, int lane, int K, int ns, int b0,
+                                         int ntile, uint32_t& hf_par) {
+  if (i >= ntile) return;
+  float* STG = reinterpret_cast<float*>(base + OFF_STG);
+  const uint32_t xs = smem_u32(base) + OFF_X;
+  const int T = a.T, PADR = a.padr, Lw = a.padr + T, spt = a.spt;
+  const int nst = min(spt, ns - i * spt), sg0 = i * spt;          // my streams: sg0 .. sg0 + nst
+  const int njobs = a.nblocks * nst;
+  const bool have_cache = a.in_cache != nullptr;
+  // landing slots of tile t: the streams' share of the NSLOT slots (each tile at least one; ns <= NSLOT: one per stream)
+  int slot0 = 0, nsl = 1;
+  {
+    int used = 0;
+    for (int t = 0; t < ntile; ++t) {
+      const int n_t = min(spt, ns - t * spt);
+      int want = ns <= NSLOT ? n_t : max(1, (NSLOT * n_t) / ns);
+      const int left = NSLOT - used - (ntile - 1 - t);               // keep one slot for every later tile
+      if (want > left) want = left;
+      if (t == i) { slot0 = used; nsl = want; }
+      used += want;
+    }
+  }
+  auto issue_tma = [&](int k) {                    // lane 0; job k = (blk, my m-th stream)
+    const int blk = k / nst, sg = sg0 + (k - blk * nst);
+    const int pad = a.dil[blk] * (K - 1);
+    const uint32_t slot = slot0 + (uint32_t)k % nsl;
+    mbar_arrive_expect_tx(&B.stg_bar[slot], (uint32_t)(C * pad * 4));
+    tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0 + sg) * C, &B.stg_bar[slot]);
+  };
+  if (have_cache && lane == 0)
+    for (int k0 = 0; k0 < nsl && k0 < njobs; ++k0) issue_tma(k0);
+  int k = 0;
+  for (int blk = 0; blk < a.nblocks; ++blk) {
+    const int pad = a.dil[blk] * (K - 1);
+    // lane -> (column j of the slice, channel-quad sub-index): four loads down the slot's channel rows, one
+    // STS.128 = 4 channels of one column of X
+    const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
+    const int j = lane & (jpl - 1), qs = lane >> lgj;
+    // X's pad columns of the tile are free once DW + cache stores (blk-1) are done (at blk 0: from the start)
+    if (blk > 0) {
+      if (lane == 0) mbar_wait_backoff(&B.h_free[i], hf_par & 1);
+      hf_par ^= 1u;
+      __syncwarp();
+    }
+    for (int sg = sg0; sg < sg0 + nst; ++sg, ++k) {
+      const int colb = sg * Lw + PADR - pad;       // first cache column of this stream for this block
+      if (have_cache) {
+        const uint32_t use = (uint32_t)k, slot = slot0 + use % nsl;
+        if (lane == 0) mbar_wait_backoff(&B.stg_bar[slot], (use / nsl) & 1);
+        __syncwarp();
+        const float* src = STG + slot * STG_FLOATS + j;
+        const uint32_t col = (uint32_t)(colb + j);
+        const uint32_t tcol = xs + (col << 8) + ((col & 7u) << 4);
+#pragma unroll 4
+        for (int cq = qs; cq < 16; cq += qstep) {
+          const float* s4 = src + 4 * cq * pad;
+          const float a0 = s4[0], a1 = s4[pad], a2 = s4[2 * pad], a3 = s4[3 * pad];
+          sts_2x2((tcol ^ ((uint32_t)(cq >> 1) << 4)) + (uint32_t)(cq & 1) * 128u, pack2(a0, a1), pack2(a2, a3));
+        }
+        __syncwarp();                              // every lane has read the slot
+        if (lane == 0 && k + nsl < njobs) {        // refill it: the same ring position, nsl jobs ahead
+          fence_proxy_async();                     // the slot was read through the generic proxy; TMA rewrites it
+          issue_tma(k + nsl);
+        }
+      } else {
+        const f32x2 z = 0ull;
+        for (int e = lane; e < pad * 16; e += 32) sts_2x2(xs + ((uint32_t)colb << 8) + 16u * (uint32_t)e, z, z);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&B.halo_bar[i]);    // the tile's slices of this block are in place
+  }
+  // DW of the last block still signals h_free: consume it so the parity stays in step
+  if (lane == 0) mbar_wait_backoff(&B.h_free[i], hf_par & 1);
+  hf_par ^= 1u;
 }
 
 // KT: compile-time tap count (5 = every shipped mdtc config; 0 = read a.ktaps, taps guarded one by one)
@@ -80,24 +204,21 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   __shared__ uint64_t dw_tok[NG];                  // depthwise-phase token: passed group -> group (see the conv below)
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too (no divergence regions around the roles)
   const int T = a.T, K = KT ? KT : a.ktaps;
   const float* vec = a.vec;
 
-  float* STG = reinterpret_cast<float*>(base + OFF_STG);
-  uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
-  float* VEC = reinterpret_cast<float*>(base + OFF_VEC);
   uint32_t sbase;                                  // shared-window address of `base`, pinned in a register
   asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(base)));
   const uint32_t xs = sbase + OFF_X;
 
   if (tid == 0) {
     for (int i = 0; i < NG; ++i) {
-      mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 2); mbar_init(&a_rdy[i], 3); mbar_init(&h_free[i], 4);
-      mbar_init(&dw_tok[i], 4);
+      mbar_init(&mma_bar[i], 1); mbar_init(&halo_bar[i], 1); mbar_init(&a_rdy[i], WPG - 1); mbar_init(&h_free[i], WPG);
+      mbar_init(&dw_tok[i], WPG);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&w_bar[i], 1); mbar_init(&w_free[i], NG); mbar_init(&vec_bar[i], 1); }
-    for (int i = 0; i < NSLOT; ++i) mbar_init(&stg_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == W_WGT) tmem_alloc(&tmem_slot, TM_COLS);
@@ -105,11 +226,11 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const Bars bars{mma_bar, halo_bar, a_rdy, h_free, w_bar, w_free, vec_bar, stg_bar};
   // phase parities: every waiter keeps its own copy; all copies of a barrier advance in lock step
   uint32_t mma_par = 0, halo_par = 0, ar_par = 0, vec_par = 0, tok_par = 0;   // compute groups
   uint32_t hf_par = 0;                                               // loaders: bit i = tile i
   uint32_t w_par = 0, wf_par = 0;                                    // bit s = slot s
-  uint32_t jobctr = 0;                                               // loader: landing-slot use counter
   const uint32_t idesc = make_idesc_bf16(128, 64);
   const int natoms = (a.idim + 63) / 64;
   const int PADR = a.padr, Lw = a.padr + T;
@@ -129,9 +250,16 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
     const int ntile = (ns + spt - 1) / spt;
     auto tile_streams = [&](int i) { return min(spt, ns - i * spt); };  // streams of tile i (sequential fill)
 
+    // the landing slots are dealt out per pass (by stream count): their barriers start every pass from phase 0
+    if (tid == 0) {
+      for (int i = 0; i < NSLOT; ++i) mbar_init(&stg_bar[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
     if (warp < NCW) {
-      // ================================================================== COMPUTE GROUPS (4 warps per tile)
-      const int grp = warp >> 2, q = warp & 3, row = 32 * q + lane;
+      // ================================================================== COMPUTE GROUPS (WPG warps per tile)
+      // warp = grp * WPG + 4 g + q: q = warp % 4 is the TMEM lane quarter the hardware lets this warp touch
+      const int grp = warp / WPG, q = warp & 3, g = (warp % WPG) >> 2, wq = warp % WPG, row = 32 * q + lane;
       if (grp < ntile) {
         const int nst = tile_streams(grp), rows = nst * T;
         const bool live = row < rows, q_live = 32 * q < rows;
@@ -166,7 +294,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (q != 0) {
+          if (wq != 0) {
             if (lane == 0) mbar_arrive(&a_rdy[grp]);
             return;
           }
@@ -204,7 +332,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         if (q_live) {
           const int nch = ((a.idim + 15) >> 4) * 2;        // 16-byte chunks incl. zero padding to a K step
           const float* src0 = a.feats + (size_t)(b0 + sg) * a.feat_bstride + (size_t)tt * a.idim;
-          for (int ch = 0; ch < nch; ++ch) {
+          for (int ch = g; ch < nch; ch += NCG) {
             float v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = 0.f;
@@ -229,8 +357,8 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         // ---- x = relu(D + bp) -> X                                            (subsampling.py:53-57)
         wait_mma();
         if (q_live) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          {
+            const int half = g;
             uint32_t d[32];
             tmem_ld32_nowait(tm_row + 32 * half, d);
             tmem_ld_wait();
@@ -278,7 +406,8 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               tj[j] = xs + (cj << 8) + ((cj & 7u) << 4);
             }
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
+            for (int mi = 0; mi < 8 / NCG; ++mi) {
+              const int m = (8 / NCG) * g + mi;
               f32x2 acc0, acc1, acc2, acc3;
               lds_2x2(vb + (uint32_t)(8 * m) * 4, acc0, acc1);          // folded depthwise bias (VEC holds only this now)
               lds_2x2(vb + (uint32_t)(8 * m) * 4 + 16, acc2, acc3);
@@ -321,7 +450,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
             const int j = lane & (jpl - 1), qs = lane >> lgj, per = 16 >> (5 - lgj);      // quads passes per stream
             const int nitem = nst * per;
-            for (int it = q; it < nitem; it += 4) {
+            for (int it = wq; it < nitem; it += WPG) {
               const int s2 = it / per, cq = (it - s2 * per) * qstep + qs;
               const int sg2 = grp * spt + s2;
               const uint32_t cc = (uint32_t)(sg2 * Lw + PADR + T - pad + j);
@@ -338,27 +467,27 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             if (lane == 0) mbar_arrive(&h_free[grp]);      // the tile's cache columns may be overwritten
           }
           // ---------------- h = relu(D + b1) -> operand rows in TMEM                          (mdtc.py:115)
+          // (16 accumulator columns at a time: this thread's 32 channels in two rounds, 72 registers per thread)
           wait_mma();
           if (q_live) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t dd[32];
-              tmem_ld32_nowait(tm_row + 32 * half, dd);
-              tmem_ld_wait();
-              uint32_t h[16], l[16];
+            for (int hh = 0; hh < 2; ++hh) {
+              float dd[16];
+              tmem_ld16(tm_row + 32 * g + 16 * hh, dd);
+              uint32_t h[8], l[8];
 #pragma unroll
-              for (int mm = 0; mm < 4; ++mm) {
-                const ulonglong2 ba = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 5 + 8 * half + 2 * mm]);      // b1
-                const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 5 + 8 * half + 2 * mm + 1]);
-                const f32x2 b0v = ba.x, b1v = ba.y, b2v = bb.x, b3v = bb.y;
-                auto E = [&](int u) { return __uint_as_float(dd[8 * mm + u]); };
-                split_pair_rz_relu(add2(pack2(E(0), E(1)), b0v), h[4 * mm + 0], l[4 * mm + 0]);
-                split_pair_rz_relu(add2(pack2(E(2), E(3)), b1v), h[4 * mm + 1], l[4 * mm + 1]);
-                split_pair_rz_relu(add2(pack2(E(4), E(5)), b2v), h[4 * mm + 2], l[4 * mm + 2]);
-                split_pair_rz_relu(add2(pack2(E(6), E(7)), b3v), h[4 * mm + 3], l[4 * mm + 3]);
+              for (int mm = 0; mm < 2; ++mm) {
+                const int m = 4 * g + 2 * hh + mm;
+                const ulonglong2 ba = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 5 + 2 * m]);      // b1
+                const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 5 + 2 * m + 1]);
+                const float* e = dd + 8 * mm;
+                split_pair_rz_relu(add2(pack2(e[0], e[1]), ba.x), h[4 * mm + 0], l[4 * mm + 0]);
+                split_pair_rz_relu(add2(pack2(e[2], e[3]), ba.y), h[4 * mm + 1], l[4 * mm + 1]);
+                split_pair_rz_relu(add2(pack2(e[4], e[5]), bb.x), h[4 * mm + 2], l[4 * mm + 2]);
+                split_pair_rz_relu(add2(pack2(e[6], e[7]), bb.y), h[4 * mm + 3], l[4 * mm + 3]);
               }
-              tmem_st16(tm_row + TM_AHI + 16 * half, h);
-              tmem_st16(tm_row + TM_ALO + 16 * half, l);
+              tmem_st8(tm_row + TM_AHI + 16 * g + 8 * hh, h);
+              tmem_st8(tm_row + TM_ALO + 16 * g + 8 * hh, l);
             }
           }
           hand_over(1);
@@ -366,26 +495,24 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           wait_mma();                                                          // (mdtc.py:116-118, 266-273)
           if (q_live) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t dd[32];
-              tmem_ld32_nowait(tm_row + 32 * half, dd);
-              tmem_ld_wait();
+            for (int hh = 0; hh < 2; ++hh) {
+              float dd[16];
+              tmem_ld16(tm_row + 32 * g + 16 * hh, dd);
 #pragma unroll
-              for (int mm = 0; mm < 4; ++mm) {
-                const int m = 4 * half + mm;
+              for (int mm = 0; mm < 2; ++mm) {
+                const int m = 4 * g + 2 * hh + mm;
                 const uint32_t ax = t_own ^ ((uint32_t)m << 4);
                 const ulonglong2 ba = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 6 + 2 * m]);                  // b2
                 const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(&a.cw[blk][16 * 6 + 2 * m + 1]);
-                const f32x2 b0v = ba.x, b1v = ba.y, b2v = bb.x, b3v = bb.y;
                 f32x2 r0, r1, r2, r3;
                 lds_2x2(ax, r0, r1);
                 lds_2x2(ax + 128, r2, r3);
-                auto E = [&](int u) { return __uint_as_float(dd[8 * mm + u]); };
+                const float* e = dd + 8 * mm;
                 float o[8];
-                unpack2(add2(add2(pack2(E(0), E(1)), b0v), r0), o[0], o[1]);
-                unpack2(add2(add2(pack2(E(2), E(3)), b1v), r1), o[2], o[3]);
-                unpack2(add2(add2(pack2(E(4), E(5)), b2v), r2), o[4], o[5]);
-                unpack2(add2(add2(pack2(E(6), E(7)), b3v), r3), o[6], o[7]);
+                unpack2(add2(add2(pack2(e[0], e[1]), ba.x), r0), o[0], o[1]);
+                unpack2(add2(add2(pack2(e[2], e[3]), ba.y), r1), o[2], o[3]);
+                unpack2(add2(add2(pack2(e[4], e[5]), bb.x), r2), o[4], o[5]);
+                unpack2(add2(add2(pack2(e[6], e[7]), bb.y), r3), o[6], o[7]);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.f);
                 if (live) {
@@ -396,9 +523,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             }
             if (stack_end) {
               // the classifier is linear: W_c (sum of stack outputs) = sum of W_c (stack output).  A compact loop over
-              // the row just written (own stores, program order) instead of 8 unrolled copies inside the epilogue
+              // the half row just written (own stores, program order) instead of unrolled copies inside the epilogue
 #pragma unroll 1
-              for (int m = 0; m < 8; ++m) {
+              for (int mi = 0; mi < 8 / NCG; ++mi) {
+                const int m = (8 / NCG) * g + mi;
                 const uint32_t ax = t_own ^ ((uint32_t)m << 4);
                 f32x2 r0, r1, r2, r3;
                 lds_2x2(ax, r0, r1);
@@ -426,8 +554,25 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           mbar_wait(&dw_tok[0], tok_par);
           tok_par ^= 1;
         }
-        // ---- classifier bias + activation: the row's sums are complete in registers
-        if (live) {
+        // ---- classifier bias + activation: the g = 1 half parks its partial sums in the row's own (now dead) X column,
+        // the g = 0 half adds them and writes the posterior
+        if (NCG > 1) {
+          if (g == 1 && live) {
+            sts_2x2(t_own, pack2(part[0], part[1]), pack2(part[2], part[3]));
+            sts_2x2(t_own + 128, pack2(part[4], part[5]), pack2(part[6], part[7]));
+          }
+          group_barrier(grp);
+          if (g == 0 && live) {
+            f32x2 p0, p1, p2, p3;
+            lds_2x2(t_own, p0, p1);
+            lds_2x2(t_own + 128, p2, p3);
+            float o[8];
+            unpack2(p0, o[0], o[1]); unpack2(p1, o[2], o[3]); unpack2(p2, o[4], o[5]); unpack2(p3, o[6], o[7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[j] += o[j];
+          }
+        }
+        if (live && g == 0) {
           float* o = a.out + (size_t)(b0 + sg) * a.out_bstride + (size_t)tt * a.odim;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -438,7 +583,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             }
           }
         }
-      } else if (q == 0 && lane == 0) {
+      } else if (wq == 0 && lane == 0) {
         // a group without streams in this pass still releases every weight slot use (w_free counts NG arrivals)
         mbar_wait(&w_bar[0], w_par & 1);
         mbar_arrive(&w_free[0]);
@@ -452,102 +597,9 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           }
       }
     } else if (warp == W_WGT) {
-      // ================================================================== WEIGHT / VECTOR RING (lane 0 works)
-      if (lane == 0) {
-        auto load_w = [&](int slot, const uint8_t* src) {
-          mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
-          bulk_g2s(Wslot[slot], src, W_SLOT, &w_bar[slot]);
-        };
-        auto load_vec = [&](int blk) {               // folded depthwise bias of block blk -> VEC[blk & 1]
-          mbar_arrive_expect_tx(&vec_bar[blk & 1], (uint32_t)(C * 4));
-          bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, vec + a.v_blocks + blk * a.v_blk_stride + K * C, (uint32_t)(C * 4),
-                   &vec_bar[blk & 1]);
-        };
-        auto wait_free = [&](int slot) {             // every tile's MMAs on the slot's current weights are done
-          mbar_wait_backoff(&w_free[slot], (wf_par >> slot) & 1);
-          wf_par ^= 1u << slot;
-        };
-        load_vec(0);
-        if (a.nblocks > 1) load_vec(1);
-        load_w(0, a.wimg);
-        if (natoms > 1) load_w(1, a.wimg + W_SLOT);
-        // slot 0 carries: Linear atom 0, W1(0), W1(1), ...; slot 1: [Linear atom 1], W2(0), W2(1), ...
-        for (int b = 0; b <= a.nblocks; ++b) {
-          const uint8_t* wb = a.wimg + (size_t)(2 + 2 * b) * W_SLOT;
-          wait_free(0);
-          if (b < a.nblocks) load_w(0, wb);
-          // every tile has handed over DW(b-1), hence finished block b-2: VEC[b & 1] is free
-          if (b >= 2 && b < a.nblocks) load_vec(b);
-          if (b > 0 || natoms > 1) wait_free(1);
-          if (b < a.nblocks) load_w(1, wb + W_SLOT);
-        }
-      }
+      if (lane == 0) weights_role(a, base, bars, K, natoms, wf_par);
     } else {
-      // ================================================================== LOADER WARPS
-      // loader l owns the streams sg with sg % 2 == l.  Per (block, stream): one 2-D TMA copy [64][pad] into a
-      // landing slot, then the warp transposes it into the pad columns in front of the stream's frames in X.
-      const int l = warp - W_LD;
-      const int nmine = (ns - l + 1) / 2;              // my streams: l, l + 2, ...
-      const int njobs = a.nblocks * nmine;
-      const bool have_cache = a.in_cache != nullptr;
-      const int nsl = l == 0 ? 4 : 3, slot0 = l == 0 ? 0 : 4;   // my landing slots: a ring of nsl
-      auto issue_tma = [&](int k) {                    // lane 0; job k = (blk, my m-th stream)
-        const int blk = k / nmine, sg = l + 2 * (k - blk * nmine);
-        const int pad = a.dil[blk] * (K - 1);
-        const uint32_t slot = slot0 + (jobctr + (uint32_t)k) % nsl;
-        mbar_arrive_expect_tx(&stg_bar[slot], (uint32_t)(C * pad * 4));
-        tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0 + sg) * C, &stg_bar[slot]);
-      };
-      if (have_cache && lane == 0)
-        for (int k0 = 0; k0 < nsl - 1 && k0 < njobs; ++k0) issue_tma(k0);
-      int k = 0;
-      for (int blk = 0; blk < a.nblocks; ++blk) {
-        const int pad = a.dil[blk] * (K - 1);
-        // lane -> (column j of the slice, channel-quad sub-index): four loads down the slot's channel rows, one
-        // STS.128 = 4 channels of one column of X
-        const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
-        const int j = lane & (jpl - 1), qs = lane >> lgj;
-        for (int i = 0; i < ntile; ++i) {
-          // X's pad columns of tile i are free once DW + cache stores (i, blk-1) are done (at blk 0: from the start)
-          if (blk > 0) {
-            if (lane == 0) mbar_wait_backoff(&h_free[i], (hf_par >> i) & 1);
-            hf_par ^= 1u << i;
-            __syncwarp();
-          }
-          for (int sg = i * spt; sg < i * spt + tile_streams(i); ++sg) {
-            if ((sg & 1) != l) continue;
-            if (have_cache && lane == 0 && k + nsl - 1 < njobs) issue_tma(k + nsl - 1);   // reuses the slot of job k-1: drained
-            const int colb = sg * Lw + PADR - pad;       // first cache column of this stream for this block
-            if (have_cache) {
-              const uint32_t use = jobctr + (uint32_t)k, slot = slot0 + use % nsl;
-              if (lane == 0) mbar_wait_backoff(&stg_bar[slot], (use / nsl) & 1);
-              __syncwarp();
-              const float* src = STG + slot * STG_FLOATS + j;
-              const uint32_t col = (uint32_t)(colb + j);
-              const uint32_t tcol = xs + (col << 8) + ((col & 7u) << 4);
-#pragma unroll 4
-              for (int cq = qs; cq < 16; cq += qstep) {
-                const float* s4 = src + 4 * cq * pad;
-                const float a0 = s4[0], a1 = s4[pad], a2 = s4[2 * pad], a3 = s4[3 * pad];
-                sts_2x2((tcol ^ ((uint32_t)(cq >> 1) << 4)) + (uint32_t)(cq & 1) * 128u, pack2(a0, a1), pack2(a2, a3));
-              }
-            } else {
-              const f32x2 z = 0ull;
-              for (int e = lane; e < pad * 16; e += 32) sts_2x2(xs + ((uint32_t)colb << 8) + 16u * (uint32_t)e, z, z);
-            }
-            fence_proxy_async();                     // the slot was read through the generic proxy; TMA rewrites it
-            ++k;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&halo_bar[i]);  // my share of tile i's slices is in place (count 2: both loaders)
-        }
-      }
-      if (have_cache) jobctr += (uint32_t)njobs;
-      // DW of the last block still signals h_free: consume it so the parities stay in step
-      for (int i = 0; i < ntile; ++i) {
-        if (lane == 0) mbar_wait_backoff(&h_free[i], (hf_par >> i) & 1);
-        hf_par ^= 1u << i;
-      }
+      loader_role(a, base, bars, warp - W_LD, lane, K, ns, b0, ntile, hf_par);
     }
     __syncthreads();       // pass boundary: X, the landing slots and the rings are reused
   }

@@ -22,6 +22,7 @@
 #include "tcn_tc.h"
 #include "dstcn_tc.h"
 #include "fsmn.h"
+#include "linear_tc.h"
 
 namespace wekws {
 
@@ -102,6 +103,13 @@ struct wekws_model {
   bool ds_ok = false;                       // tensor-core path for the depthwise-separable TCN (hidden 256)
   DsTcArgs dsargs{};
   FsmnArgs fsmn{};                          // FSMN backbone (fsmn.cu): weights live in h_vec / d_vec
+  bool cls_tc = false;                      // wide classifier head (odim > 4) as its own tcgen05 GEMM (linear_tc.cu)
+  std::vector<uint8_t> h_cimg;              //   behind the tensor-core DS-TCN backbone
+  std::vector<float> h_cbias;
+  uint8_t* d_cimg = nullptr;
+  float* d_cbias = nullptr;
+  float* d_hidden = nullptr;                // (B, T, 256) scratch between the two kernels; grows monotonically
+  size_t hidden_cap = 0;
   bool gru_tc_ok = false;                   // cluster / tensor-core GRU (gru_tc.cu): images live in h_wimg / d_wimg
   GruTcArgs grutc{};
 };
@@ -239,7 +247,9 @@ void pack_tc(wekws_model* m) {
   m->tc_ok = false;
   m->tcn_ok = false;
   m->ds_ok = false;
+  m->cls_tc = false;
   m->h_wimg.clear();
+  m->h_cimg.clear();
   const wekws_model_config& c = m->cfg;
   if (c.backbone == WEKWS_BACKBONE_DSTCN) {
     DsTcArgs& t = m->dsargs;
@@ -250,8 +260,19 @@ void pack_tc(wekws_model* m) {
     t.v_mean = a.v_mean; t.v_istd = a.v_istd; t.v_bp = a.v_bp; t.v_blocks = a.v_blocks;
     t.v_blk_stride = a.v_blk_stride; t.v_wc = a.v_wc; t.v_bc = a.v_bc;
     for (int b = 0; b < a.nblocks; ++b) { t.dil[b] = a.dil[b]; t.coff[b] = a.coff[b]; }
-    if (!dstcn_tc_eligible(t, c.hdim)) return;
-    if (m->folded.size() != (size_t)(1 + a.nblocks)) return;
+    // output_dim > 4 (CTC vocabularies): the classifier becomes its own tensor-core GEMM fed from a hidden scratch
+    m->cls_tc = c.odim > 4 && linear_tc_eligible(c.odim, c.hdim);
+    t.hidden = m->cls_tc ? reinterpret_cast<float*>(1) : nullptr;      // placeholder for the eligibility test only
+    const bool ok = dstcn_tc_eligible(t, c.hdim);
+    t.hidden = nullptr;
+    if (!ok) { m->cls_tc = false; return; }
+    if (m->folded.size() != (size_t)(1 + a.nblocks)) { m->cls_tc = false; return; }
+    if (m->cls_tc) {        // W_c^T [256][odim] sits in h_vec at v_wc (pack_classifier), the bias at v_bc
+      m->h_cimg.assign(linear_tc_image_bytes(c.odim, c.hdim), 0);
+      linear_tc_pack(m->h_cimg.data(), m->h_vec.data() + a.v_wc, c.odim, c.odim, c.hdim, bf16_rn, bf16_to_f);
+      m->h_cbias.assign((size_t)((c.odim + 127) / 128) * 128, 0.f);
+      for (int j = 0; j < c.odim; ++j) m->h_cbias[j] = m->h_vec[a.v_bc + j];
+    }
     const int natoms = (a.idim + 63) / 64;
     m->h_wimg.assign((size_t)(2 * natoms + 8 * a.nblocks) * 32768, 0);
     uint8_t* dst = m->h_wimg.data();
@@ -554,7 +575,9 @@ int pack_fsmn(wekws_model* m) {
 
 void free_device(wekws_model* m) {
   cudaFree(m->d_stream); cudaFree(m->d_vec); cudaFree(m->d_chunk_off); cudaFree(m->d_wimg);
+  cudaFree(m->d_cimg); cudaFree(m->d_cbias); cudaFree(m->d_hidden);
   m->d_stream = nullptr; m->d_vec = nullptr; m->d_chunk_off = nullptr; m->d_wimg = nullptr;
+  m->d_cimg = nullptr; m->d_cbias = nullptr; m->d_hidden = nullptr; m->hidden_cap = 0;
 }
 
 }  // namespace
@@ -635,6 +658,12 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
       m->tcargs.wimg = m->d_wimg; m->tcargs.vec = m->d_vec;
       m->tcnargs.wimg = m->d_wimg; m->tcnargs.vec = m->d_vec;
       m->dsargs.wimg = m->d_wimg; m->dsargs.vec = m->d_vec;
+    }
+    if (m->cls_tc) {
+      WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_cimg, m->h_cimg.size()));
+      WEKWS_CUDA_OK(cudaMemcpy(m->d_cimg, m->h_cimg.data(), m->h_cimg.size(), cudaMemcpyHostToDevice));
+      WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_cbias, m->h_cbias.size() * sizeof(float)));
+      WEKWS_CUDA_OK(cudaMemcpy(m->d_cbias, m->h_cbias.data(), m->h_cbias.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     m->conv_max_T = conv_backbone_max_T(m->conv, m->padmax);
     WEKWS_REQUIRE(m->conv_max_T >= 1, "model does not fit the fused kernel's shared memory");
@@ -732,6 +761,16 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
     const bool use_tcn = m->tcn_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
     const bool use_ds = m->ds_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
     const int maxT = use_tc ? tc_max_T() : use_tcn ? tcn_tc_max_T() : use_ds ? dstcn_tc_max_T() : m->conv_max_T;
+    if (use_ds && m->cls_tc) {      // hidden scratch between the backbone kernel and the classifier GEMM
+      const size_t need = (size_t)B * (size_t)T * (size_t)m->cfg.hdim;
+      if (need > m->hidden_cap) {
+        WEKWS_CUDA_OK(cudaStreamSynchronize(st));          // the old scratch may still be in use on this stream
+        cudaFree(m->d_hidden);
+        m->d_hidden = nullptr; m->hidden_cap = 0;
+        WEKWS_CUDA_OK(cudaMalloc((void**)&m->d_hidden, need * sizeof(float)));
+        m->hidden_cap = need;
+      }
+    }
     const int nchunk = (int)((T + maxT - 1) / maxT);
     const int Tc = (int)((T + nchunk - 1) / nchunk);
     for (int64_t t0 = 0; t0 < T; t0 += Tc) {
@@ -759,6 +798,7 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
         a.T = (int)(T - t0 < Tc ? T - t0 : Tc);
         a.feat_bstride = T * m->cfg.idim;
         a.out_bstride = T * m->cfg.odim;
+        if (m->cls_tc) { a.hidden = m->d_hidden + t0 * m->cfg.hdim; a.hidden_bstride = T * m->cfg.hdim; }
         int rc = dstcn_tc_launch(a, st);
         if (rc) return rc;
         continue;
@@ -790,6 +830,16 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
       if (rc) return rc;
     }
   }
+  if (m->cfg.backbone == WEKWS_BACKBONE_DSTCN && m->cls_tc && m->ds_ok && m->precision == 0 && T >= 8 &&
+      ((uintptr_t)d_feats & 15) == 0) {
+    // classifier (+ activation) of all B*T frames in one tensor-core GEMM over the hidden scratch (classifier.py:63-67)
+    LinearTcArgs a;
+    a.x = m->d_hidden; a.out = d_out; a.wimg = m->d_cimg; a.bias = m->d_cbias;
+    a.rows = B * T; a.x_stride = m->cfg.hdim; a.out_stride = m->cfg.odim;
+    a.N = m->cfg.odim; a.K = m->cfg.hdim; a.act = m->cfg.activation; a.n_mtiles = 0;
+    int rc = linear_tc_launch(a, st);
+    if (rc) return rc;
+  }
   if (flags & WEKWS_FWD_SOFTMAX) {
     const long long rows = B * T;
     const int wpb = 8;
@@ -808,8 +858,43 @@ extern "C" int wekws_pipeline_forward(wekws_fbank* fb, wekws_model* m, const voi
   WEKWS_REQUIRE(wekws_fbank_feature_dim(fb) == m->cfg.idim, "pipeline: the front-end produces %d features but the model expects input_dim %d",
                 wekws_fbank_feature_dim(fb), m->cfg.idim);
   const int64_t frames = wekws_fbank_num_frames(fb, num_samples);
+  // The feature tensor only lives between the two launches.  Pin it in L2 for their duration (persisting access-policy
+  // window on this stream): the front-end's writes stay in the cache, the model kernel's first-Linear reads hit there,
+  // and the lines are released (not written back as "persisting") afterwards -- the 320 B/frame never has to make the
+  // HBM round trip as long as B * frames * idim * 4 fits the device's persisting-L2 carve-out.
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t feat_bytes = (size_t)B * (size_t)frames * (size_t)m->cfg.idim * sizeof(float);
+  bool windowed = false;
+  if (feat_bytes > 0) {
+    int dev = 0, max_persist = 0, max_window = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess && max_persist > 0) {
+      static bool limit_set[64] = {false};
+      if (dev >= 0 && dev < 64 && !limit_set[dev]) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        limit_set[dev] = true;
+      }
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = d_feat_scratch;
+      attr.accessPolicyWindow.num_bytes = feat_bytes < (size_t)max_window ? feat_bytes : (size_t)max_window;
+      attr.accessPolicyWindow.hitRatio = feat_bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)feat_bytes;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      windowed = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    }
+    cudaGetLastError();      // the window is an optimisation: never fatal
+  }
   int rc = wekws_fbank_forward(fb, d_pcm, pcm_dtype, B, num_samples, pcm_stride, nullptr, nullptr, nullptr,
                                d_feat_scratch, frames, stream);
-  if (rc) return rc;
-  return wekws_model_forward(m, d_feat_scratch, d_in_cache, d_out, d_out_cache, B, frames, flags, stream);
+  if (rc == 0) rc = wekws_model_forward(m, d_feat_scratch, d_in_cache, d_out, d_out_cache, B, frames, flags, stream);
+  if (windowed) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;                       // window off for whatever the caller runs next
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+  }
+  return rc;
 }
