@@ -50,12 +50,12 @@ constexpr int X_BYTES = XCOLS * 256;       // 129024: X[col][64] fp32
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
 constexpr int NSLOT = 7;                   // TMA landing slots, shared out among the tiles' loaders by stream count
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
-constexpr int VEC_FLOATS = 64;             // per-block vector kept in shared memory: the folded depthwise bias
+constexpr int VEC_FLOATS = 64;             // per-block vector kept in shared memory: the folded depthwise bias (all blocks preloaded)
 constexpr int OFF_X = 0;
 constexpr int OFF_STG = OFF_X + X_BYTES;                   // 129024
 constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 186368 (1024-aligned: SWIZZLE_128B images)
 constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 219136
-constexpr int SMEM_TOTAL = OFF_VEC + 2 * VEC_FLOATS * 4 + 1024;   // 224256 incl. alignment slack
+constexpr int SMEM_TOTAL = OFF_VEC + kTcMaxBlocks * VEC_FLOATS * 4 + 1024;   // 224512 incl. alignment slack
 static_assert(OFF_W % 1024 == 0, "weight images must be 1024-byte aligned");
 static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 // TMEM columns of tile i: [160 i, 160 i + 64) accumulator, + 64.. A hi (<= 48 cols = K 96), + 112.. A lo
@@ -81,32 +81,29 @@ struct Bars {
 };
 
 // WEIGHT / VECTOR RING (one thread): slot 0 carries Linear atom 0, W1(0), W1(1), ...; slot 1 [Linear atom 1], W2(0), ...
-__device__ __noinline__ void weights_role(const TcArgs& a, uint8_t* base, Bars B, int K, int natoms, uint32_t& wf_par) {
+__device__ __noinline__ void weights_role(const TcArgs& a, uint8_t* base, Bars B, int K, int natoms, uint32_t& wf_par,
+                                          bool first_pass) {
   uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
   float* VEC = reinterpret_cast<float*>(base + OFF_VEC);
   auto load_w = [&](int slot, const uint8_t* src) {
     mbar_arrive_expect_tx(&B.w_bar[slot], W_SLOT);
     bulk_g2s(Wslot[slot], src, W_SLOT, &B.w_bar[slot]);
   };
-  auto load_vec = [&](int blk) {               // folded depthwise bias of block blk -> VEC[blk & 1]
-    mbar_arrive_expect_tx(&B.vec_bar[blk & 1], (uint32_t)(C * 4));
-    bulk_g2s(VEC + (blk & 1) * VEC_FLOATS, a.vec + a.v_blocks + blk * a.v_blk_stride + K * C, (uint32_t)(C * 4),
-             &B.vec_bar[blk & 1]);
-  };
+  if (first_pass) {                            // folded depthwise biases of ALL blocks, once per launch -> VEC[blk]
+    mbar_arrive_expect_tx(&B.vec_bar[0], (uint32_t)(a.nblocks * C * 4));
+    for (int blk = 0; blk < a.nblocks; ++blk)
+      bulk_g2s(VEC + blk * VEC_FLOATS, a.vec + a.v_blocks + blk * a.v_blk_stride + K * C, (uint32_t)(C * 4), &B.vec_bar[0]);
+  }
   auto wait_free = [&](int slot) {             // every tile's MMAs on the slot's current weights are done
     mbar_wait_backoff(&B.w_free[slot], (wf_par >> slot) & 1);
     wf_par ^= 1u << slot;
   };
-  load_vec(0);
-  if (a.nblocks > 1) load_vec(1);
   load_w(0, a.wimg);
   if (natoms > 1) load_w(1, a.wimg + W_SLOT);
   for (int b = 0; b <= a.nblocks; ++b) {
     const uint8_t* wb = a.wimg + (size_t)(2 + 2 * b) * W_SLOT;
     wait_free(0);
     if (b < a.nblocks) load_w(0, wb);
-    // every tile has handed over DW(b-1), hence finished block b-2: VEC[b & 1] is free
-    if (b >= 2 && b < a.nblocks) load_vec(b);
     if (b > 0 || natoms > 1) wait_free(1);
     if (b < a.nblocks) load_w(1, wb + W_SLOT);
   }
@@ -382,11 +379,13 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         // ---- blocks
         for (int blk = 0; blk < a.nblocks; ++blk) {
           const int d = a.dil[blk], pad = d * (K - 1);
-          const uint32_t vb = vsm + (uint32_t)(blk & 1) * (VEC_FLOATS * 4);
+          const uint32_t vb = vsm + (uint32_t)blk * (VEC_FLOATS * 4);
           const bool stack_end = (blk > 0) && (blk % a.stack_size == 0);
           // ---------------- depthwise dilated conv (+folded BN) -> operand rows in TMEM      (mdtc.py:56-57)
-          mbar_wait(&vec_bar[blk & 1], (vec_par >> (blk & 1)) & 1);
-          vec_par ^= 1u << (blk & 1);
+          if (vec_par == 0) {                 // the biases of all blocks land once per launch
+            mbar_wait(&vec_bar[0], 0);
+            vec_par = 1;
+          }
           mbar_wait(&halo_bar[grp], halo_par);
           halo_par ^= 1;
           // The depthwise conv is the shared-memory-bandwidth phase (22 LDS.128 per 8 channels) while the epilogues and
@@ -597,7 +596,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           }
       }
     } else if (warp == W_WGT) {
-      if (lane == 0) weights_role(a, base, bars, K, natoms, wf_par);
+      if (lane == 0) weights_role(a, base, bars, K, natoms, wf_par, b0 == sb);
     } else {
       loader_role(a, base, bars, warp - W_LD, lane, K, ns, b0, ntile, hf_par);
     }
