@@ -7,12 +7,15 @@
 // (kaldi.py:183-211), |rfft|^2 (kaldi.py:616-618), sparse triangular mel projection
 // (kaldi.py:436-511, 630), log(max(., eps)) (kaldi.py:633).
 //
-// One warp owns one frame.  The 512-point real FFT is a 256-point complex FFT of the
+// One warp owns one frame for the FFT.  The 512-point real FFT is a 256-point complex FFT of the
 // even/odd packed frame, done as a radix-8 / radix-8 / radix-4 Stockham autosort with the
 // first radix-8 entirely in registers (lane p holds z[p + 32 r]) and two exchanges through
 // bank-conflict-free padded per-warp shared buffers; lane-constant twiddles live in
 // registers.  A CTA (8 warps) stages the 5360 samples its 32 consecutive frames need once
-// (coalesced), so each PCM byte is read from HBM ~1.05x and each output byte written once.
+// (16-byte loads), so each PCM byte is read from HBM ~1.05x and each output byte written once.
+// The mel projection runs after all 32 power spectra of the work item are in shared memory, with
+// lane = frame and the (warp-uniform) sparse row of one mel bin per warp: no divergence between
+// lanes whatever the filter widths, 3 instructions per tap per 32 frames.
 #include <math.h>
 #include <vector>
 
@@ -30,6 +33,12 @@ constexpr int FB_NT = FB_WARPS * 32;
 using fbcore::WIN; using fbcore::SHIFT; using fbcore::NFFT; using fbcore::NBIN; using fbcore::A_SZ; using fbcore::B_SZ;
 constexpr int STAGE = (FB_FRAMES - 1) * SHIFT + WIN;  // 5360 samples
 constexpr int MAX_MEL = 128;
+constexpr int P_ST = NBIN + 1;              // row pitch of the power-spectrum tile (odd: lane = frame reads are conflict-free)
+constexpr int O_ST = MAX_MEL + 1;           // row pitch of the output staging tile (aliases the PCM stage)
+static_assert(FB_FRAMES == 32, "the mel phase maps one frame to one lane");
+static_assert(FB_FRAMES * O_ST <= STAGE, "output staging must fit in the PCM stage");
+static_assert(STAGE % 8 == 0, "vector staging");
+constexpr int SMEM_FLOATS_COMMON = STAGE + FB_WARPS * 2 * (A_SZ + B_SZ) + 2 * NBIN + WIN + 2 * NBIN + 64 + 3 * MAX_MEL;
 
 struct FbankArgs {
   const void* pcm;
@@ -41,6 +50,7 @@ struct FbankArgs {
   int nmel;
   float preemph, log_floor;
   int remove_dc;
+  int vec_ok;               // every stream starts 16-byte aligned: stage PCM with 16-byte loads
   // tables (device)
   const float2* tw256;     // W_256^j
   const float2* tw512;     // W_512^k, k < 256
@@ -68,11 +78,16 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
   float2* s_tw512 = reinterpret_cast<float2*>(s_stage + STAGE + FB_WARPS * 2 * (A_SZ + B_SZ));
   float2* s_win = s_tw512 + NBIN;
   float* s_mw = reinterpret_cast<float*>(s_win + WIN / 2);               // [2 * NBIN + 64]
+  int* s_mtab = reinterpret_cast<int*>(s_mw + 2 * NBIN + 64);            // [3][MAX_MEL]: first bin, count, offset into s_mw
+  float* s_pow = reinterpret_cast<float*>(s_mtab + 3 * MAX_MEL);         // [FB_FRAMES][P_ST] (log-mel kernel only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < NBIN; i += FB_NT) s_tw512[i] = a.tw512[i];
   for (int i = tid; i < WIN / 2; i += FB_NT) s_win[i] = make_float2(a.window[2 * i], a.window[2 * i + 1]);
   for (int i = tid; i < a.mw_total; i += FB_NT) s_mw[i] = a.mw[i];
+  for (int i = tid; i < a.nmel; i += FB_NT) {
+    s_mtab[i] = a.mstart[i]; s_mtab[MAX_MEL + i] = a.mcnt[i]; s_mtab[2 * MAX_MEL + i] = a.moff[i];
+  }
 
   fbcore::LaneTwiddles tw;
   tw.load(a.tw256, lane);
@@ -93,13 +108,82 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
     __syncthreads();
     {
       const PCM* src = reinterpret_cast<const PCM*>(a.pcm) + b * a.pcm_stride;
-      const long long base = f0 * SHIFT;
-      for (int i = tid; i < STAGE; i += FB_NT) {
-        const long long n = base + i;
-        s_stage[i] = n < len ? (float)src[n] : 0.f;
+      const long long base = f0 * SHIFT;            // multiple of 160 samples: 16-byte aligned when the stream is
+      constexpr int VW = 16 / (int)sizeof(PCM);     // samples per 16-byte load
+      if (a.vec_ok) {
+        for (int i = tid; i < STAGE / VW; i += FB_NT) {
+          const long long n = base + (long long)i * VW;
+          float* d = s_stage + i * VW;
+          if (n + VW <= len) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + n));
+            if (sizeof(PCM) == 2) {
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+              float f[8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                f[2 * k] = (float)(int16_t)(w[k] & 0xffffu);
+                f[2 * k + 1] = (float)((int32_t)w[k] >> 16);
+              }
+              reinterpret_cast<float4*>(d)[0] = make_float4(f[0], f[1], f[2], f[3]);
+              reinterpret_cast<float4*>(d)[1] = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              reinterpret_cast<float4*>(d)[0] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y),
+                                                            __uint_as_float(v.z), __uint_as_float(v.w));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < VW; ++k) d[k] = n + k < len ? (float)src[n + k] : 0.f;
+          }
+        }
+      } else {
+        for (int i = tid; i < STAGE; i += FB_NT) {
+          const long long n = base + i;
+          s_stage[i] = n < len ? (float)src[n] : 0.f;
+        }
       }
     }
     __syncthreads();
+
+    if (!MFCC) {
+      // ---- power spectra of the item's 32 frames -> s_pow ----
+      for (int fi = 0; fi < FB_FPW; ++fi) {
+        const int fl = warp + FB_WARPS * fi;
+        if (f0 + fl < mb) {
+          const float* s = s_stage + fl * SHIFT;
+          fbcore::frame_power_spectrum([&](int n) { return s[n]; }, s_win, s_tw512, tw, Ar, Ai, Br, Bi, s_pow + fl * P_ST,
+                                       a.preemph, a.remove_dc, lane);
+        }
+      }
+      __syncthreads();                              // spectra complete; the PCM stage is dead and becomes the output tile
+      // ---- mel projection (sparse rows, kaldi.py:630), log floor, CMVN: lane = frame, one mel bin per warp at a time.
+      // Rows of absent frames hold stale values; they are never stored.
+      float* s_o = s_stage;
+      {
+        const float* prow = s_pow + lane * P_ST;
+        for (int m = warp; m < a.nmel; m += FB_WARPS) {
+          const int st = s_mtab[m], cnt = s_mtab[MAX_MEL + m];
+          const float* w = s_mw + s_mtab[2 * MAX_MEL + m];
+          const float* p = prow + st;
+          float e = 0.f;
+#pragma unroll 4
+          for (int i = 0; i < cnt; ++i) e = fmaf(w[i], p[i], e);
+          float v = logf(fmaxf(e, a.log_floor));
+          if (a.mean) v -= __ldg(a.mean + m);
+          if (a.istd) v *= __ldg(a.istd + m);
+          s_o[lane * O_ST + m] = v;
+        }
+      }
+      __syncthreads();
+      for (int fi = 0; fi < FB_FPW; ++fi) {
+        const int fl = warp + FB_WARPS * fi;
+        const long long f = f0 + fl;
+        if (f >= a.max_frames) continue;
+        float* outp = a.out + (b * a.max_frames + f) * a.odim;
+        const bool live = f < mb;
+        for (int m = lane; m < a.nmel; m += 32) outp[m] = live ? s_o[fl * O_ST + m] : 0.f;
+      }
+      continue;                                     // the barrier at the top of the loop protects s_o
+    }
 
     float lm[FB_FPW][4];                          // MFCC: log-mel rows of this warp's frames (0 for absent frames)
     uint32_t fvalid = 0;
@@ -120,21 +204,10 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
     }
 
     const float* s = s_stage + fl * SHIFT;
-    fbcore::frame_power_spectrum([&](int n) { return s[n]; }, s_win, s_tw512, tw, Ar, Ai, Br, Bi, a.preemph, a.remove_dc, lane);
+    fbcore::frame_power_spectrum([&](int n) { return s[n]; }, s_win, s_tw512, tw, Ar, Ai, Br, Bi, Br, a.preemph, a.remove_dc, lane);
     __syncwarp();
-    // ---- mel projection (sparse rows), log floor, CMVN ----
-    if (!MFCC) {
-      for (int m = lane; m < a.nmel; m += 32) {
-        const int st = __ldg(a.mstart + m), cnt = __ldg(a.mcnt + m);
-        const float* w = s_mw + __ldg(a.moff + m);
-        float e = 0.f;
-        for (int i = 0; i < cnt; ++i) e = fmaf(w[i], Br[st + i], e);
-        float v = logf(fmaxf(e, a.log_floor));
-        if (a.mean) v -= __ldg(a.mean + m);
-        if (a.istd) v *= __ldg(a.istd + m);
-        outp[m] = v;
-      }
-    } else {
+    // ---- mel projection (sparse rows), log floor ----
+    {
       fvalid |= 1u << fi;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -329,14 +402,16 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.dct = fb->d_dct; a.lifter = fb->d_lifter; a.nceps = fb->nceps;
   a.odim = fb->nceps > 0 ? fb->nceps : fb->cfg.num_mel_bins;
   const long long items = B * ((max_frames + FB_FRAMES - 1) / FB_FRAMES);
-  const size_t smem = (size_t)(STAGE + FB_WARPS * 2 * (A_SZ + B_SZ) + 2 * NBIN + WIN + 2 * NBIN + 64) * sizeof(float);
+  const bool mf = fb->nceps > 0;
+  const size_t smem = (size_t)(SMEM_FLOATS_COMMON + (mf ? 0 : FB_FRAMES * P_ST)) * sizeof(float);
+  const int esz = pcm_dtype == WEKWS_PCM_S16 ? 2 : 4;
+  a.vec_ok = (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0 && ((pcm_stride * esz) & 15) == 0;
   int dev = 0;
   WEKWS_CUDA_OK(cudaGetDevice(&dev));
   WEKWS_REQUIRE(dev == fb->device, "fbank handle was created on device %d but the current device is %d", fb->device, dev);
   WEKWS_REQUIRE(dev >= 0 && dev < 64, "fbank: device index %d out of range", dev);
   static int occ_dev[64][4] = {};        // the shared-memory attribute and the occupancy are per device
   int* occ = occ_dev[dev];
-  const bool mf = fb->nceps > 0;
   const int ti = (pcm_dtype == WEKWS_PCM_S16 ? 0 : 1) + (mf ? 2 : 0);
   const void* kern = ti == 0 ? (const void*)fbank_kernel<int16_t, false> : ti == 1 ? (const void*)fbank_kernel<float, false>
                    : ti == 2 ? (const void*)fbank_kernel<int16_t, true> : (const void*)fbank_kernel<float, true>;

@@ -55,13 +55,13 @@ struct LaneTwiddles {
   }
 };
 
-// Power spectrum of one frame -> Br[0..255].  `s(n)`: sample n (0..399) of the frame as float (int16 scale).
-// Ar/Ai: A_SZ floats each, Br/Bi: B_SZ floats each, private to the warp.  s_win: window as (even, odd) pairs; s_tw512:
+// Power spectrum of one frame -> pw[0..255].  `s(n)`: sample n (0..399) of the frame as float (int16 scale).
+// Ar/Ai: A_SZ floats each, Br/Bi: B_SZ floats each, private to the warp; pw may be Br.  s_win: window as (even, odd) pairs; s_tw512:
 // W_512^k, k < 256.  All 32 lanes participate.
 template <typename Sample>
 __device__ __forceinline__ void frame_power_spectrum(Sample s_, const float2* __restrict__ s_win,
                                                      const float2* __restrict__ s_tw512, const LaneTwiddles& tw, float* Ar,
-                                                     float* Ai, float* Br, float* Bi, float preemph, int remove_dc, int lane) {
+                                                     float* Ai, float* Br, float* Bi, float* pw, float preemph, int remove_dc, int lane) {
   const float* t1r = tw.t1r; const float* t1i = tw.t1i; const float* t2r = tw.t2r; const float* t2i = tw.t2i;
     // ---- window: lane owns packed points m = lane + 32 i (even/odd sample pair 2m, 2m+1) ----
     float xa[7], xb[7], xc[7];
@@ -137,7 +137,7 @@ __device__ __forceinline__ void frame_power_spectrum(Sample s_, const float2* __
       Ar[piA(q + 192)] = d0r - d1i;  Ai[piA(q + 192)] = d0i + d1r;    // d0 + i d1
     }
     __syncwarp();
-    // ---- real-FFT untangle + power spectrum -> Br[0..255] ----
+    // ---- real-FFT untangle + power spectrum -> pw[0..255] ----
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = lane + 32 * i;
@@ -149,7 +149,7 @@ __device__ __forceinline__ void frame_power_spectrum(Sample s_, const float2* __
       const float2 w = s_tw512[k];
       const float p = w.x * dr - w.y * di, q = w.x * di + w.y * dr;
       const float xr = er + q, xi = ei - p;
-      Br[k] = xr * xr + xi * xi;
+      pw[k] = xr * xr + xi * xi;
     }
     __syncwarp();
 }
