@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define WEKWS_B200_ABI_VERSION 3   /* 2: + wekws_fbank_set_mfcc, wekws_fbank_feature_dim, wekws_det_stats; 3: det max_score is double */
+#define WEKWS_B200_ABI_VERSION 4   /* 2: + wekws_fbank_set_mfcc, wekws_fbank_feature_dim, wekws_det_stats; 3: det max_score is double; 4: precision mode 2, wekws_model_uses_tensor_cores_bt */
 
 #if defined(__GNUC__)
 #define WEKWS_API __attribute__((visibility("default")))
@@ -158,10 +158,14 @@ WEKWS_API int wekws_model_finalize(wekws_model* m);
 /* Arithmetic of the dense GEMMs: 0 = auto (default): tcgen05 tensor cores with a 3-pass bf16
  * operand split (~2^-17 relative, posteriors within 1e-5 of fp32) where a fused tensor-core
  * kernel exists (mdtc / dense tcn with hidden 64, ds_tcn with hidden 256 and k = 8; chunk >= 8 frames),
- * FP32 FMA elsewhere; 1 = FP32 FMA only. */
+ * FP32 FMA elsewhere; the GRU (hidden 128, 1-2 layers) has a weight-streaming tcgen05 kernel that auto picks by batch
+ * and chunk (>= 640 streams at T = 1, >= 400 at T = 2..7, >= 256 at T >= 8) and the FP32 kernel otherwise; 1 = FP32 FMA only;
+ * 2 = the tensor-core kernel wherever one exists, whatever the batch (tests, benchmarks). */
 WEKWS_API int wekws_model_set_precision(wekws_model* m, int mode);
-/* 1 if a forward with T frames per call runs the tcgen05 kernel (after finalize), else 0.    */
+/* 1 if a forward with T frames per call runs the tcgen05 kernel (after finalize), else 0.  The plain form answers for
+ * a large batch; the GRU's choice also depends on the batch B.                               */
 WEKWS_API int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T);
+WEKWS_API int wekws_model_uses_tensor_cores_bt(const wekws_model* m, int64_t B, int64_t T);
 /* Debug/test accessors of the packed host-side program (valid after finalize).      */
 WEKWS_API int64_t wekws_model_packed_floats(const wekws_model* m, int which /*0 stream, 1 vectors, 2 tensor-core weight images (bytes / 4)*/);
 WEKWS_API int wekws_model_packed_copy(const wekws_model* m, int which, float* h_dst, int64_t capacity);

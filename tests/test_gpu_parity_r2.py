@@ -365,26 +365,31 @@ def test_ctc_decode_large_vocabulary_matches_oracle():
     assert nhit >= B // 2
 
 
-@pytest.mark.parametrize("B,T", [(70, 40), (1, 1), (512, 3), (1300, 2)])
-def test_gru_cluster_tensor_core_path(B, T):
-    """The 8-CTA-cluster tcgen05 GRU (hidden units split over the cluster, h exchanged through distributed shared
-    memory) against the oracle and against the FP32 kernel: ragged tiles (B not a multiple of 64), more tiles than
-    clusters, random h0, CMVN, two outputs."""
-    cfg, m, sd = _model("gru", cmvn=True, input_dim=40, output_dim=2)
-    x = synth.features(B, T, 40, seed=5, cmvn_like=True)
+@pytest.mark.parametrize("B,T,idim", [(70, 40, 40), (1, 1, 40), (512, 3, 80), (1300, 2, 40), (9600, 1, 80), (33, 7, 72)])
+def test_gru_tensor_core_path(B, T, idim):
+    """The weight-streaming tcgen05 GRU (gru_tc.cu: transposed GEMMs, units on the TMEM lanes) against the oracle and
+    against the FP32 kernel: ragged tiles (B not a multiple of 64), more tiles than SMs, one and two feature K slabs,
+    random h0, CMVN, two outputs."""
+    cfg, m, sd = _model("gru", cmvn=True, input_dim=idim, output_dim=2)
+    x = synth.features(B, T, idim, seed=5, cmvn_like=True)
     h0 = torch.randn(2, B, 128, generator=torch.Generator().manual_seed(8)) * 0.5
     try:
         m.precision = "fp32"
         y32, h32 = m(x.to(DEV), h0.to(DEV))
         assert not m.uses_tensor_cores(T)
-        m.precision = "auto"
+        m.precision = "tensor"                      # the tcgen05 kernel whatever the batch ("auto" picks by B and T)
         ytc, htc = m(x.to(DEV), h0.to(DEV))
-        assert m.uses_tensor_cores(T)
-    finally:
+        assert m.uses_tensor_cores(T, B)
         m.precision = "auto"
+        assert m.uses_tensor_cores(T, B) == (B >= (640 if T == 1 else 400 if T < 8 else 256))
+        ya, ha = m(x.to(DEV), h0.to(DEV))
+        assert torch.equal(ya, ytc if m.uses_tensor_cores(T, B) else y32)
+        m.precision = "tensor"
+    finally:
+        pass
     y_ref, h_ref = O.kws_forward(sd, cfg, x, h0)
     e32, etc = float((y32.cpu() - y_ref).abs().max()), float((ytc.cpu() - y_ref).abs().max())
-    print(f"gru B={B} T={T}: posterior max-abs fp32 kernel {e32:.2e}, cluster/tensor-core kernel {etc:.2e}")
+    print(f"gru B={B} T={T} idim={idim}: posterior max-abs fp32 kernel {e32:.2e}, tensor-core kernel {etc:.2e}")
     assert e32 <= TOL_POST and etc <= TOL_POST
     assert float((htc.cpu() - h_ref).abs().max()) <= TOL_POST and float((h32.cpu() - h_ref).abs().max()) <= TOL_POST
     # streaming: T calls of one frame == one call of T frames (state carried)
@@ -392,6 +397,7 @@ def test_gru_cluster_tensor_core_path(B, T):
     for t in range(T):
         yt, hd = m(x[:, t:t + 1].to(DEV), hd)
         ys.append(yt)
+    m.precision = "auto"
     assert float((torch.cat(ys, 1) - ytc).abs().max()) <= 2e-5 and float((hd - htc).abs().max()) <= 2e-5
 
 

@@ -18,7 +18,7 @@ BACKBONE_MDTC, BACKBONE_TCN, BACKBONE_DSTCN, BACKBONE_GRU, BACKBONE_FSMN = 0, 1,
 ACT_IDENTITY, ACT_SIGMOID = 0, 1
 PCM_S16, PCM_F32 = 0, 1
 FWD_SOFTMAX = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class FbankConfig(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "wekws_model_finalize": (C.c_int, [C.c_void_p]),
     "wekws_model_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "wekws_model_uses_tensor_cores": (C.c_int, [C.c_void_p, C.c_int64]),
+    "wekws_model_uses_tensor_cores_bt": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "wekws_model_packed_floats": (C.c_int64, [C.c_void_p, C.c_int]),
     "wekws_model_packed_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "wekws_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

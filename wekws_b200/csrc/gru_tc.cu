@@ -1,18 +1,26 @@
-// Tensor-core GRU forward on 8-CTA clusters (KWSModel.forward with the GRU backbone, kws_model.py:128-133; PyTorch gate
-// order r, z, n -- see gru.cu for the FP32 reference kernel of the same math).
+// Tensor-core GRU forward with weight streaming (KWSModel.forward with the GRU backbone, kws_model.py:128-133; PyTorch
+// gate order r, z, n -- see gru.cu for the FP32 kernel of the same math).
 //
-// Why clusters: at the streaming shape (B = 512 streams, one frame per call) the FP32 kernel makes every SM stream all
-// 786 KB of weights out of L2 for 0.2 GFLOP of math -- 116 MB of L2 egress per 20 us step.  Here a cluster of 8 CTAs
-// owns a tile of 64 streams and SPLITS THE HIDDEN UNITS: CTA r keeps only the weights of units [16r, 16r+16) of both
-// layers (48 gate rows x 256 inputs per layer, as pre-swizzled bf16 hi|lo images, 104 KB) resident in shared memory for
-// the whole launch, computes those units for all 64 streams on tcgen05 (M = 128 rows of which 64 are streams, N = 48,
-// bf16 x3 split, fp32 accumulate in TMEM), and hands the new h values to its 7 peers through distributed shared
-// memory -- each value is split into bf16 hi/lo once, by its producer, and stored straight into the K-major
-// SWIZZLE_128B operand image every CTA's next GEMM reads.  Per step and CTA: 99 MMAs, 96 remote 16-byte stores per
-// stream row, three cluster barriers; no weight byte moves after the prologue.
+// Shape of the problem at the streaming operating point (B = 512 streams, one frame per call): 0.2 GFLOP against 786 KB
+// of weights.  The FP32 kernel spreads the streams over all 148 SMs, so every SM pulls all weights out of L2 for 3-4
+// streams: 116 MB of L2 egress and ~20 us per step, and its FMA loop is bound by shared-memory operand loads.  Here a
+// CTA owns a tile of 64 streams and the GEMMs are TRANSPOSED: D^T[gate row][stream] = W[gate row][k] * X^T[k][stream],
+// i.e. the weights are the M = 128 operand (one gate of all 128 hidden units per MMA row block, streamed from L2 through
+// a ring of 16 KB pre-swizzled bf16 hi|lo chunks by bulk async copies), the activations are the N = 64 operand (K-major
+// SWIZZLE_128B images in shared memory: features, x0, h of each layer, each split into bf16 hi + lo once by its producer)
+// and the accumulators put the hidden UNITS on the 128 TMEM lanes -- so the gate math runs on all four SM sub-partitions
+// with one thread per (unit, 32 streams), the old h stays in fp32 registers for the whole call, and no CTA ever talks to
+// another one.  fp32 parity through the bf16 x3 split (W_hi X_hi + W_hi X_lo + W_lo X_hi, fp32 accumulate).
 //
-// Roles (128 threads): warps 0-1 own the 64 stream rows (TMEM lanes 0..63): feature split, gate math, exchanges,
-// classifier; warp 2 lane 0 issues the MMAs; warp 3 loads the weight images (bulk async copies) in the prologue.
+// Per step and CTA: (2 ceil(idim/64) + 24 L) weight chunks = 786 KB for the shipped model, ~300 MMAs (M128 N64 K16),
+// TMEM: layer l accumulators at columns [256 l, 256 l + 256) = r | z | n_x | n_h (64 streams each); the preprocessing
+// Linear borrows layer 0's n_h block.  Measured dead end this replaces: hidden units split over an 8-CTA cluster with
+// resident weights and DSMEM exchange of h -- three cluster barriers per step made it slower than the FP32 kernel
+// (profiles/r02_gru_notes.md).
+//
+// Warps (384 threads): 0-7 unit owners (TMEM lane quadrant w % 4, stream half w / 4): epilogues, gate math, classifier,
+// cache I/O; 8 MMA issue (one lane); 9 weight ring (one lane); 10-11 feature rows -> operand image for the next step.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,166 +32,266 @@ namespace {
 
 using namespace tc;
 
-constexpr int CL = 8;                 // CTAs per cluster == hidden-unit slices
-constexpr int M = 64;                 // streams per cluster tile
-constexpr int H = 128, UPC = H / CL;  // hidden units, units per CTA (16)
-constexpr int NG = 3 * UPC;           // gate columns per CTA (48)
-constexpr int NT = 128;
-constexpr int SLAB = 8192;            // one operand K-slab image: 64 rows x 128 B (rows 64..127 of the M=128 MMA alias the next slab)
-// shared memory map (bytes, all 1024-aligned)
-constexpr int OFF_AX = 0;                         // X0 image: [slab 0 hi][slab 0 lo][slab 1 hi][slab 1 lo]
-constexpr int OFF_AH = OFF_AX + 4 * SLAB;         // H images of layer l at OFF_AH + l * 4 * SLAB
-constexpr int OFF_GUARD = OFF_AH + 2 * 4 * SLAB;  // 8 KB the last slab's phantom rows may read
-constexpr int OFF_WP = OFF_GUARD + SLAB;          // Wp slice: [slab 0 hi][slab 0 lo][slab 1 hi][slab 1 lo], 16 rows x 128 B each
-constexpr int WP_SLAB = 16 * 128;
-constexpr int OFF_W = OFF_WP + 4 * WP_SLAB;       // per layer: W_ih [s0 hi][s0 lo][s1 hi][s1 lo], W_hh likewise; 48 rows x 128 B each
-constexpr int W_SLABB = NG * 128;                 // 6144
-constexpr int W_LAYER = 8 * W_SLABB;              // 49152
-constexpr int OFF_HOWN = OFF_W + 2 * W_LAYER;     // fp32 h of this CTA's units: [L][M][UPC]
-constexpr int OFF_END = OFF_HOWN + 2 * M * UPC * 4;
+constexpr int M = 64;                   // streams per CTA tile (the MMA N)
+constexpr int H = 128;                  // hidden units (the MMA M)
+constexpr int NT = 384;
+constexpr int SLAB = M * 128;           // one activation K-slab image (64 rows x 128 B), 8 KB
+constexpr int IMG = 4 * SLAB;           // activation image: [slab 0 hi][slab 0 lo][slab 1 hi][slab 1 lo]
+constexpr int CHUNK = H * 128;          // one weight chunk: 128 gate rows x 64 K, bf16, 16 KB
+constexpr int NSLOT = 5;
+// shared memory map (bytes, 1024-aligned)
+constexpr int OFF_F = 0;                // feature image (K = idim <= 128)
+constexpr int OFF_X0 = OFF_F + IMG;     // x0 = relu(Linear)
+constexpr int OFF_H = OFF_X0 + IMG;     // h of layer l at OFF_H + l * IMG
+constexpr int OFF_RING = OFF_H + 2 * IMG;
+constexpr int OFF_END = OFF_RING + NSLOT * CHUNK;
 constexpr int SMEM_BYTES = OFF_END + 1024;
-static_assert(OFF_WP % 1024 == 0 && OFF_W % 1024 == 0 && W_SLABB % 1024 == 0, "operand images must be 1024-byte aligned");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
-// TMEM columns: feature operand hi [0,48) lo [48,96); accumulators D_lin [96,112), D1 = x W_ih^T [112,160),
-// D2 = h W_hh^T of layer l at [160 + 48 l, +48)
-constexpr int TM_FHI = 0, TM_FLO = 48, TM_DLIN = 96, TM_D1 = 112, TM_D2 = 160, TM_COLS = 256;
+constexpr int TM_COLS = 512;
+constexpr int TM_R = 0, TM_Z = 64, TM_NX = 128, TM_NH = 192, TM_LAYER = 256, TM_LIN = TM_NH;
 
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// byte offset of K element k (0..127) of row m inside a two-slab K-major SWIZZLE_128B operand image pair (hi image at
-// +0, lo image at +SLAB within each slab pair)
+// byte offset of K element k (0..127) of stream row m inside an activation image (hi; lo at + SLAB)
 __device__ __forceinline__ uint32_t a_off(int m, int k) {
   return (uint32_t)((k >> 6) * 2 * SLAB + m * 128 + ((((k & 63) >> 3) ^ (m & 7)) << 4) + (k & 7) * 2);
 }
+__device__ __forceinline__ void split1(float x, uint16_t& hi, uint16_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = *reinterpret_cast<const uint16_t*>(&h);
+  lo = *reinterpret_cast<const uint16_t*>(&l);
+}
+// Gates on the SFU approximations (ex2.approx, rcp.approx: ~1 ulp each): absolute error ~1e-7, far inside the
+// fp32-parity budget (posterior 1e-4), and ~25 instructions per (unit, stream) instead of ~80 with expf / tanhf / IEEE
+// division -- the gate math is on the critical path of every step.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+// sigmoid(g + b) with nb = -b * log2(e) folded by the caller: 1 / (1 + 2^(-(g + b) log2 e))
+__device__ __forceinline__ float sigmoid_fast(float g, float nb) { return rcp_fast(1.f + ex2_fast(fmaf(g, -LOG2E, nb))); }
+// tanh(t) = 1 - 2 / (1 + 2^(2 t log2 e)); the exponent is clamped so that 2^x stays finite (tanh is 1 there anyway)
+__device__ __forceinline__ float tanh_fast(float t) {
+  return fmaf(-2.f, rcp_fast(1.f + ex2_fast(fminf(t * (2.f * LOG2E), 126.f))), 1.f);
+}
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kernel(const __grid_constant__ GruTcArgs a) {
+struct Bars {
+  uint64_t w_full[NSLOT], w_free[NSLOT];
+  uint64_t f_rdy, lin_bar, x0_rdy, d_bar[2], h_rdy[2];
+};
+
+__device__ __forceinline__ void wait_flip(uint64_t* bar, uint32_t& par) {
+  mbar_wait(bar, par);
+  par ^= 1;
+}
+#ifndef GRU_TIMING
+#define GRU_TIMING 0
+#endif
+#if GRU_TIMING
+#define TWAIT(acc, stmt) { const long long t0_ = clock64(); stmt; acc += clock64() - t0_; }
+#define TSEG_BEGIN(v) const long long v = clock64();
+#define TSEG_END(acc, v) acc += clock64() - v;
+#else
+#define TWAIT(acc, stmt) { stmt; }
+#define TSEG_BEGIN(v)
+#define TSEG_END(acc, v)
+#endif
+
+// -------------------------------------------------------------------------------------------------- MMA issue (one lane)
+// Measured on B200 (tests/native/mma_rate_probe.cu): one thread dispatches an M128 x N<=96 x K16 MMA every ~55 cycles at
+// best (N = 128: 64, N = 256: 128 cycles), and only if the issue loop is a straight line of MMAs -- building a
+// descriptor per instruction doubles that.  So everything below is unrolled over precomputed 64-bit descriptors.
+struct Issuer {
+  Bars* b;
+  uint32_t idesc;
+  uint64_t wdesc0;                         // descriptor of ring slot 0 (slot s: + s * CHUNK / 16 in the address field)
+  uint32_t slot, full_par;                 // ring position (full_par: bit s = parity of the next fill of slot s)
+  long long t_w;
+  __device__ __forceinline__ uint64_t take() {             // wait for the next chunk, return its descriptor
+    TWAIT(t_w, mbar_wait(&b->w_full[slot], (full_par >> slot) & 1u));
+    tc_fence_after();
+    return wdesc0 + (uint64_t)(slot * (CHUNK >> 4));
+  }
+  __device__ __forceinline__ void release() {              // the chunk's MMAs are issued: free its slot when they finish
+    if (elect_one_sync()) umma_commit(&b->w_free[slot]);
+    full_par ^= 1u << slot;
+    slot = slot + 1 == NSLOT ? 0 : slot + 1;
+  }
+  // one K slab with `ksteps` MMA K steps: D (+)= W[:, slab] X[:, slab]^T with the x3 split
+  __device__ __forceinline__ void slab_rt(uint32_t d, uint64_t xhi, int ksteps, uint32_t& acc) {
+    const uint64_t xlo = xhi + (SLAB >> 4);
+    const uint64_t whi = take();
+    if (elect_one_sync()) {
+      for (int k = 0; k < ksteps; ++k) umma_bf16(d, whi + 2 * k, xhi + 2 * k, idesc, k == 0 ? acc : 1u);
+      for (int k = 0; k < ksteps; ++k) umma_bf16(d, whi + 2 * k, xlo + 2 * k, idesc, 1);
+    }
+    acc = 1;
+    release();
+    const uint64_t wlo = take();
+    if (elect_one_sync()) {
+      for (int k = 0; k < ksteps; ++k) umma_bf16(d, wlo + 2 * k, xhi + 2 * k, idesc, 1);
+    }
+    release();
+  }
+  // one gate block over K = 128 (two slabs of 4 K steps), fully unrolled; FRESH: the first MMA overwrites D
+  template <bool FRESH>
+  __device__ __forceinline__ void gate(uint32_t d, uint64_t ximg) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const uint64_t xhi = ximg + (uint64_t)(s * (2 * SLAB >> 4)), xlo = xhi + (SLAB >> 4);
+      const uint64_t whi = take();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, whi + 2 * k, xhi + 2 * k, idesc, (FRESH && s == 0 && k == 0) ? 0u : 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, whi + 2 * k, xlo + 2 * k, idesc, 1u);
+      }
+      release();
+      const uint64_t wlo = take();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, wlo + 2 * k, xhi + 2 * k, idesc, 1u);
+      }
+      release();
+    }
+  }
+};
+
+// executed by ALL lanes of the issue warp (uniform control flow and values); the MMAs / commits are elected
+__device__ __noinline__ void issuer_role(const GruTcArgs& a, Bars* b_, uint32_t sbase_, uint32_t tmem_, int my_tiles_) {
+  const uint32_t sbase = uniform32(sbase_), tmem = uniform32(tmem_);
+  const int my_tiles = (int)uniform32((uint32_t)my_tiles_);
+  const int L = (int)uniform32((uint32_t)a.L), T = (int)uniform32((uint32_t)a.T), idim = (int)uniform32((uint32_t)a.idim);
+  Bars* b = reinterpret_cast<Bars*>(__cvta_shared_to_generic(uniform32(smem_u32(b_))));
+  Issuer is{b, make_idesc_bf16(H, M), make_sdesc_sw128(sbase + OFF_RING), 0u, 0u, 0};
+  long long t_f = 0, t_x0 = 0, t_h0 = 0, t_h1 = 0;
+  const long long t_begin = clock64();
+  uint32_t p_f = 0, p_x0 = 0, p_h0 = 0, p_h1 = 0;
+  const int nsf = (idim + 63) >> 6;
+  const uint64_t f_img = make_sdesc_sw128(sbase + OFF_F), x0_img = make_sdesc_sw128(sbase + OFF_X0);
+  const uint64_t h0_img = make_sdesc_sw128(sbase + OFF_H), h1_img = make_sdesc_sw128(sbase + OFF_H + IMG);
+  const uint32_t d0 = tmem, d1 = tmem + TM_LAYER;
+  for (int it = 0; it < my_tiles; ++it) {
+    wait_flip(&b->h_rdy[0], p_h0);                       // initial h images of the tile
+    if (L == 2) wait_flip(&b->h_rdy[1], p_h1);
+    for (int t = 0; t < T; ++t) {
+      // ---- preprocessing Linear (subsampling.py:53-57): D_lin = Wp F^T
+      TWAIT(t_f, wait_flip(&b->f_rdy, p_f));
+      tc_fence_after();
+      {
+        uint32_t acc = 0;
+        for (int s = 0; s < nsf; ++s) {
+          const int rem = idim - 64 * s;
+          is.slab_rt(d0 + TM_LIN, f_img + (uint64_t)(s * (2 * SLAB >> 4)), rem >= 64 ? 4 : (rem + 15) >> 4, acc);
+        }
+        if (elect_one_sync()) umma_commit(&b->lin_bar);
+      }
+      // ---- layer 0: the h-parts of r and z do not need x0
+      is.gate<true>(d0 + TM_R, h0_img);
+      is.gate<true>(d0 + TM_Z, h0_img);
+      TWAIT(t_x0, wait_flip(&b->x0_rdy, p_x0));          // x0 image written, D_lin consumed
+      tc_fence_after();
+      is.gate<true>(d0 + TM_NH, h0_img);
+      is.gate<false>(d0 + TM_R, x0_img);
+      is.gate<false>(d0 + TM_Z, x0_img);
+      is.gate<true>(d0 + TM_NX, x0_img);
+      if (elect_one_sync()) umma_commit(&b->d_bar[0]);
+      if (L == 2) {
+        if (t > 0) { TWAIT(t_h1, wait_flip(&b->h_rdy[1], p_h1)); tc_fence_after(); }   // layer-1 gates of step t-1: D1 free, h1 image new
+        is.gate<true>(d1 + TM_R, h1_img);
+        is.gate<true>(d1 + TM_Z, h1_img);
+        is.gate<true>(d1 + TM_NH, h1_img);
+        TWAIT(t_h0, wait_flip(&b->h_rdy[0], p_h0));      // layer-0 gates of this step: new h0 image, D0 free
+        tc_fence_after();
+        is.gate<false>(d1 + TM_R, h0_img);
+        is.gate<false>(d1 + TM_Z, h0_img);
+        is.gate<true>(d1 + TM_NX, h0_img);
+        if (elect_one_sync()) umma_commit(&b->d_bar[1]);
+      } else {
+        TWAIT(t_h0, wait_flip(&b->h_rdy[0], p_h0));
+        tc_fence_after();
+      }
+    }
+    if (L == 2) { TWAIT(t_h1, wait_flip(&b->h_rdy[1], p_h1)); tc_fence_after(); }    // last step's layer-1 gates
+  }
+#if GRU_TIMING
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+    printf("issuer: total %lld cycles, waits: weights %lld, features %lld, x0 %lld, h0 %lld, h1 %lld\n", clock64() - t_begin, is.t_w,
+           t_f, t_x0, t_h0, t_h1);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------- weight ring (one lane)
+__device__ __noinline__ void weights_role(const GruTcArgs& a, Bars* b, uint8_t* base, int my_tiles) {
+  const int per_step = 2 * ((a.idim + 63) >> 6) + 24 * a.L;
+  const long long total = (long long)my_tiles * a.T * per_step;
+  int ci = 0;
+  uint32_t slot = 0, free_par = 0;
+  for (long long c = 0; c < total; ++c) {
+    if (c >= NSLOT) {
+      mbar_wait(&b->w_free[slot], (free_par >> slot) & 1u);
+      free_par ^= 1u << slot;
+    }
+    mbar_arrive_expect_tx(&b->w_full[slot], CHUNK);
+    bulk_g2s(base + OFF_RING + slot * CHUNK, a.wimg + (size_t)ci * CHUNK, CHUNK, &b->w_full[slot]);
+    slot = slot + 1 == NSLOT ? 0 : slot + 1;
+    ci = ci + 1 == per_step ? 0 : ci + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NT, 1) gru_tc_kernel(const __grid_constant__ GruTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  __shared__ uint64_t w_bar, mma_bar;
+  __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
   const uint32_t sbase = smem_u32(base);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x / CL, nclusters = gridDim.x / CL;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const float* vec = a.vec;
   const int L = a.L, T = a.T;
 
   if (tid == 0) {
-    mbar_init(&w_bar, 1);
-    mbar_init(&mma_bar, 1);
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bars.w_full[i], 1); mbar_init(&bars.w_free[i], 1); }
+    mbar_init(&bars.f_rdy, 2);
+    mbar_init(&bars.lin_bar, 1);
+    mbar_init(&bars.x0_rdy, 8);
+    mbar_init(&bars.d_bar[0], 1); mbar_init(&bars.d_bar[1], 1);
+    mbar_init(&bars.h_rdy[0], 8); mbar_init(&bars.h_rdy[1], 8);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_slot, TM_COLS);
+  if (warp == 8) tmem_alloc(&tmem_slot, TM_COLS);
+  // the feature image's K padding must be finite (it meets zero weights): clear it once
+  for (int i = tid; i < IMG / 16; i += NT) reinterpret_cast<uint4*>(base + OFF_F)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  // (no zero fill: rows past the tile's streams and the phantom rows 64..127 of the M = 128 MMAs only ever feed
-  // accumulator rows nobody reads -- GEMM rows are independent)
-  // ---- prologue: this rank's weight images -> shared memory (stay for the whole launch)
-  if (warp == 3 && lane == 0) {
-    const uint32_t bytes = 4 * WP_SLAB + (uint32_t)L * W_LAYER;
-    const uint8_t* src = a.wimg + (size_t)rank * (4 * WP_SLAB + 2 * W_LAYER);
-    mbar_arrive_expect_tx(&w_bar, bytes);
-    for (uint32_t o = 0; o < bytes; o += 8192) {
-      const uint32_t n = bytes - o < 8192 ? bytes - o : 8192;
-      bulk_g2s(base + OFF_WP + o, src + o, n, &w_bar);
-    }
-  }
-  fence_proxy_async();
-  __syncthreads();
-  cluster_barrier();                       // every CTA's barriers / images exist before anyone stores remotely
 
-  uint32_t mma_par = 0;
-  const uint32_t idesc48 = make_idesc_bf16(128, NG), idesc16 = make_idesc_bf16(128, UPC);
-  const int ksf = (a.idim + 15) >> 4;      // K steps of the feature GEMM
+  const int my_tiles = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  // 3-pass bf16x3 GEMM, both operands in shared memory: D (+)= A * W^T over `nslab` K-slabs of 64
-  auto gemm_ss = [&](uint32_t d_tmem, uint32_t a_img, uint32_t w_img, uint32_t w_slabb, int nslab, uint32_t idesc) {
-    uint32_t acc = 0;
-    for (int s = 0; s < nslab; ++s) {
-      const uint64_t ahi = make_sdesc_sw128(a_img + s * 2 * SLAB), alo = make_sdesc_sw128(a_img + s * 2 * SLAB + SLAB);
-      const uint64_t whi = make_sdesc_sw128(w_img + s * 2 * w_slabb), wlo = make_sdesc_sw128(w_img + s * 2 * w_slabb + w_slabb);
-      for (int k = 0; k < 4; ++k) { umma_bf16(d_tmem, ahi + 2 * k, whi + 2 * k, idesc, acc); acc = 1; }
-      for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, alo + 2 * k, whi + 2 * k, idesc, 1);
-      for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ahi + 2 * k, wlo + 2 * k, idesc, 1);
-    }
-  };
-  auto wait_mma = [&]() {
-    mbar_wait(&mma_bar, mma_par);
-    mma_par ^= 1;
-    tc_fence_after();
-  };
-  // the MMA issuer (warp 2 lane 0) runs `f` after the row owners' operands are visible; everybody then waits for it
-  auto issue = [&](auto f) {
-    tc_fence_before();
-    fence_proxy_async();                   // generic-proxy writes of the images -> async proxy (tcgen05.mma reads them)
-    __syncthreads();
-    if (warp == 2 && lane == 0) {
-      tc_fence_after();
-      f();
-      umma_commit(&mma_bar);
-    }
-    wait_mma();
-  };
-
-  for (int tile = cluster_id; tile < a.n_tiles; tile += nclusters) {
-    const int b0 = tile * M;
-    const int Mv = min(M, a.B - b0);       // valid streams of this tile
-    const bool row_owner = tid < M;
-    const int m = tid;                     // my stream row (row owners)
-    const bool live = row_owner && m < Mv;
-    float* hown = reinterpret_cast<float*>(base + OFF_HOWN);
-    // ---- initial hidden state: every CTA splits the whole tile's h into its own images; its own units also in fp32.
-    // All 128 threads: thread -> (row tid & 63, half tid >> 6 of the 128 units); the 16 float4 loads of a layer are
-    // issued together (one memory latency per layer instead of one per 8 values)
-    {
-      const int hr = tid & (M - 1), half = tid >> 6;
-      const bool hlive = hr < Mv;
-      for (int l = 0; l < L; ++l) {
-        float4 v4[16];
-        const float4* src = (a.in_cache != nullptr && hlive)
-                                ? reinterpret_cast<const float4*>(a.in_cache + ((size_t)l * a.B + b0 + hr) * H + 64 * half) : nullptr;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v4[i] = src ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        uint8_t* img = base + OFF_AH + l * 4 * SLAB;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {                 // 8 chunks of 8 units
-          const float4 p0 = v4[2 * c], p1 = v4[2 * c + 1];
-          uint4 hi, lo;
-          split2(p0.x, p0.y, hi.x, lo.x); split2(p0.z, p0.w, hi.y, lo.y);
-          split2(p1.x, p1.y, hi.z, lo.z); split2(p1.z, p1.w, hi.w, lo.w);
-          const int k0 = 64 * half + 8 * c;
-          const uint32_t off = a_off(hr, k0);
-          *reinterpret_cast<uint4*>(img + off) = hi;
-          *reinterpret_cast<uint4*>(img + off + SLAB) = lo;
-          if ((k0 >> 4) == (int)rank) {
-            float* ho = hown + (l * M + hr) * UPC + (k0 & 15);
-            *reinterpret_cast<float4*>(ho) = p0;
-            *reinterpret_cast<float4*>(ho + 4) = p1;
-          }
-        }
-      }
-    }
-    if (tile == cluster_id) mbar_wait(&w_bar, 0);      // weights landed (first tile only)
-
-    for (int t = 0; t < T; ++t) {
-      // ================= preprocessing Linear + ReLU for my 16 output units            (subsampling.py:53-57)
-      if (row_owner) {
-        const float* src0 = a.feats + ((size_t)(b0 + m) * T + t) * a.idim;
-        // the whole feature row in flight at once (idim <= 96: 24 float4), then CMVN + split chunk by chunk
+  if (warp == 8) {
+    issuer_role(a, &bars, sbase, tmem, my_tiles);
+  } else if (warp == 9) {
+    if (lane == 0) weights_role(a, &bars, base, my_tiles);
+  } else if (warp >= 10) {
+    // ---- feature rows: thread = stream row; CMVN (cmvn.py:45-47), bf16 hi|lo split, 16-byte chunks into the image
+    const int m = tid - 320;
+    uint32_t p_lin = 0;
+    long long step = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b0 = (blockIdx.x + it * gridDim.x) * a.ms;
+      const bool live = m < a.ms && b0 + m < a.B;
+      for (int t = 0; t < T; ++t, ++step) {
         float4 f4[24];
-        const bool vec4 = (a.idim & 3) == 0 && (reinterpret_cast<uintptr_t>(src0) & 15) == 0;
+        const float* src0 = a.feats + ((size_t)(b0 + m) * T + t) * a.idim;
+        const bool vec4 = (a.idim & 3) == 0 && (reinterpret_cast<uintptr_t>(a.feats) & 15) == 0;
 #pragma unroll
         for (int i = 0; i < 24; ++i) {
           f4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -197,9 +305,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
             }
           }
         }
+        if (step > 0) wait_flip(&bars.lin_bar, p_lin);     // the previous step's Linear has read the image
 #pragma unroll
         for (int ch = 0; ch < 12; ++ch) {
-          if (ch < 2 * ksf) {
+          if (8 * ch < a.idim) {
             float v[8] = {f4[2 * ch].x, f4[2 * ch].y, f4[2 * ch].z, f4[2 * ch].w,
                           f4[2 * ch + 1].x, f4[2 * ch + 1].y, f4[2 * ch + 1].z, f4[2 * ch + 1].w};
             const int k0 = 8 * ch;
@@ -208,197 +317,246 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) gru_tc_kerne
               for (int u = 0; u < 8; ++u)
                 if (k0 + u < a.idim) v[u] = (v[u] - __ldg(vec + a.v_mean + k0 + u)) * __ldg(vec + a.v_istd + k0 + u);
             }
-            uint32_t h4[4], l4[4];
-            split2(v[0], v[1], h4[0], l4[0]); split2(v[2], v[3], h4[1], l4[1]);
-            split2(v[4], v[5], h4[2], l4[2]); split2(v[6], v[7], h4[3], l4[3]);
-            const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
-            tmem_st4(trow + TM_FHI + 4 * ch, h4);
-            tmem_st4(trow + TM_FLO + 4 * ch, l4);
+            const uint32_t off = a_off(m, k0);
+            split_store8(v, base + OFF_F, base + OFF_F + SLAB, off);
           }
         }
-        tmem_st_wait();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.f_rdy);
       }
-      // One issue for everything that does not depend on this step's exchanges: the Linear and the h-parts gh = h W_hh^T
-      // of BOTH layers (they read the previous step's h images), so only the x-parts sit on the critical path later
-      issue([&]() {
-        const uint32_t d = tmem + TM_DLIN;
-        uint32_t acc = 0;
-        for (int s = 0; s * 4 < ksf; ++s) {
-          const int ks = min(4, ksf - 4 * s);
-          const uint64_t whi = make_sdesc_sw128(sbase + OFF_WP + s * 2 * WP_SLAB), wlo = make_sdesc_sw128(sbase + OFF_WP + s * 2 * WP_SLAB + WP_SLAB);
-          for (int k = 0; k < ks; ++k) { umma_bf16_ts(d, tmem + TM_FHI + 32 * s + 8 * k, whi + 2 * k, idesc16, acc); acc = 1; }
-          for (int k = 0; k < ks; ++k) umma_bf16_ts(d, tmem + TM_FLO + 32 * s + 8 * k, whi + 2 * k, idesc16, 1);
-          for (int k = 0; k < ks; ++k) umma_bf16_ts(d, tmem + TM_FHI + 32 * s + 8 * k, wlo + 2 * k, idesc16, 1);
-        }
-        for (int l = 0; l < L; ++l)
-          gemm_ss(tmem + TM_D2 + NG * l, sbase + OFF_AH + l * 4 * SLAB, sbase + OFF_W + l * W_LAYER + 4 * W_SLABB, W_SLABB, 2, idesc48);
-      });
-      // x0 of my units -> every CTA's X0 image (the previous step's layer-0 GEMMs are long done: five barriers ago)
-      if (row_owner) {
-        float d[16];
-        tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + TM_DLIN, d);
-        uint32_t hi[8], lo[8];
+    }
+  } else {
+    // ---- unit owners: thread = (hidden unit j, 32 streams)
+    const int q = warp & 3, sh = warp >> 2;
+    const int j = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const int s0 = 32 * sh;                                  // first stream of this thread
+    // image address pieces of K element j: row m adds m * 128 and flips the 16-byte chunk by (m & 7)
+    const uint32_t kbase = (uint32_t)((j >> 6) * 2 * SLAB + (j & 7) * 2);
+    const uint32_t kc16 = (uint32_t)(((j & 63) >> 3) << 4);
+    uint32_t p_lin = 0, p_d0 = 0, p_d1 = 0, p_h = 0;
+    float hreg[2][32];
+    long long t_lin = 0, t_d0 = 0, t_d1 = 0, t_cls = 0, s_pro = 0, s_x0 = 0, s_g0 = 0, s_g1 = 0, s_cls = 0, s_fin = 0;
+    const long long t_begin = clock64();
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b0 = (blockIdx.x + it * gridDim.x) * a.ms;
+      const int Mv = min(a.ms, a.B - b0);                    // live streams of the tile (rows Mv.. of the images are never read back)
+      const int nchunk = Mv <= s0 ? 0 : Mv - s0 <= 16 ? 1 : 2;   // 16-stream chunks of this thread that hold live streams
+      // ---- initial hidden state -> fp32 registers + operand images
+      TSEG_BEGIN(tp0)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float x0 = fmaxf(d[2 * u] + __ldg(vec + a.v_bp + UPC * rank + 2 * u), 0.f);
-          const float x1 = fmaxf(d[2 * u + 1] + __ldg(vec + a.v_bp + UPC * rank + 2 * u + 1), 0.f);
-          split2(x0, x1, hi[u], lo[u]);
-        }
-        const uint32_t o0 = sbase + OFF_AX + a_off(m, UPC * rank), o1 = sbase + OFF_AX + a_off(m, UPC * rank + 8);
+      for (int l = 0; l < 2; ++l) {                          // compile-time l: hreg stays in registers
+        if (l >= L) break;
+        {
+          const float* hin = a.in_cache != nullptr ? a.in_cache + ((size_t)l * a.B + b0 + s0) * H + j : nullptr;
+          const int nlive = hin != nullptr ? Mv - s0 : 0;    // streams of this thread that exist
 #pragma unroll
-        for (uint32_t p = 0; p < CL; ++p) {
-          const uint32_t r0 = map_to_cta(o0, p), r1 = map_to_cta(o1, p);
-          st_cluster_v4(r0, hi[0], hi[1], hi[2], hi[3]); st_cluster_v4(r1, hi[4], hi[5], hi[6], hi[7]);
-          st_cluster_v4(r0 + SLAB, lo[0], lo[1], lo[2], lo[3]); st_cluster_v4(r1 + SLAB, lo[4], lo[5], lo[6], lo[7]);
+          for (int i = 0; i < 32; ++i) hreg[l][i] = i < nlive ? __ldg(hin + i * H) : 0.f;
         }
+        uint8_t* img = base + OFF_H + l * IMG + kbase;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c >= nchunk) break;
+#pragma unroll
+          for (int i = 16 * c; i < 16 * c + 16; ++i) {
+            uint16_t hi, lo;
+            split1(hreg[l][i], hi, lo);
+            const uint32_t off = (uint32_t)((s0 + i) * 128) + (kc16 ^ (uint32_t)((i & 7) << 4));
+            *reinterpret_cast<uint16_t*>(img + off) = hi;
+            *reinterpret_cast<uint16_t*>(img + off + SLAB) = lo;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.h_rdy[l]);
       }
-      tc_fence_before();
-      cluster_barrier();                   // X0 complete in every CTA; every CTA's h-part GEMMs have read the old h images
-
-      // ================= GRU layers
-      for (int l = 0; l < L; ++l) {
-        const uint32_t x_img = l == 0 ? sbase + OFF_AX : sbase + OFF_AH + (l - 1) * 4 * SLAB;
-        const uint32_t h_img = sbase + OFF_AH + l * 4 * SLAB;
-        const uint32_t w_l = sbase + OFF_W + l * W_LAYER;
-        issue([&]() { gemm_ss(tmem + TM_D1, x_img, w_l, W_SLABB, 2, idesc48); });       // gi = x W_ih^T (my 48 gate rows)
-        uint32_t hi[8], lo[8];
-        if (row_owner) {
-          const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
-          float gi[48], gh[16];
-          tmem_ld16(trow + TM_D1, *reinterpret_cast<float(*)[16]>(&gi[0]));
-          tmem_ld16(trow + TM_D1 + 16, *reinterpret_cast<float(*)[16]>(&gi[16]));
-          tmem_ld16(trow + TM_D1 + 32, *reinterpret_cast<float(*)[16]>(&gi[32]));
-          const float* bih = vec + a.v_layers + (size_t)l * a.v_layer_stride + 2 * H * 3 * H;   // b_ih (384) then b_hh (384)
-          const float* bhh = bih + 3 * H;
-          float rg[16];
-          const uint32_t td2 = trow + TM_D2 + NG * l;
-          tmem_ld16(td2, gh);                                                           // r gate
+      TSEG_END(s_pro, tp0)
+      wait_flip(&bars.h_rdy[L - 1], p_h);                    // (keeps this thread's phase count of the barrier in step)
+      const float bp = __ldg(vec + a.v_bp + j);
+      for (int t = 0; t < T; ++t) {
+        // ================= x0 = relu(Linear + b)  -> X0 image
+        TWAIT(t_lin, wait_flip(&bars.lin_bar, p_lin));
+        tc_fence_after();
+        TSEG_BEGIN(tx0)
+        {
+          uint8_t* img = base + OFF_X0 + kbase;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int j = UPC * rank + u;
-            rg[u] = sigmoidf_acc(gi[u] + __ldg(bih + j) + gh[u] + __ldg(bhh + j));
-          }
-          float zg[16];
-          tmem_ld16(td2 + 16, gh);                                                      // z gate
+          for (int c = 0; c < 2; ++c) {
+            if (c >= nchunk) break;
+            float d[16];
+            tmem_ld16(trow + TM_LIN + s0 + 16 * c, d);
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int j = H + UPC * rank + u;
-            zg[u] = sigmoidf_acc(gi[16 + u] + __ldg(bih + j) + gh[u] + __ldg(bhh + j));
-          }
-          tmem_ld16(td2 + 32, gh);                                                      // n gate
-          float* ho = hown + (l * M + m) * UPC;
-          float hn[16];
-#pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int j = 2 * H + UPC * rank + u;
-            const float n = tanhf(gi[32 + u] + __ldg(bih + j) + rg[u] * (gh[u] + __ldg(bhh + j)));
-            hn[u] = (1.f - zg[u]) * n + zg[u] * ho[u];
-            ho[u] = hn[u];
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) split2(hn[2 * u], hn[2 * u + 1], hi[u], lo[u]);
-        }
-        // (the old h image was last read by the h-part GEMMs issued at the top of the step, which every CTA finished
-        // before the X0 barrier; layer 1's x-part reads the NEW h0 image, after the barrier below)
-        if (row_owner) {
-          const uint32_t o0 = h_img + a_off(m, UPC * rank), o1 = h_img + a_off(m, UPC * rank + 8);
-#pragma unroll
-          for (uint32_t p = 0; p < CL; ++p) {
-            const uint32_t r0 = map_to_cta(o0, p), r1 = map_to_cta(o1, p);
-            st_cluster_v4(r0, hi[0], hi[1], hi[2], hi[3]); st_cluster_v4(r1, hi[4], hi[5], hi[6], hi[7]);
-            st_cluster_v4(r0 + SLAB, lo[0], lo[1], lo[2], lo[3]); st_cluster_v4(r1 + SLAB, lo[4], lo[5], lo[6], lo[7]);
+            for (int i = 0; i < 16; ++i) {
+              uint16_t hi, lo;
+              split1(fmaxf(d[i] + bp, 0.f), hi, lo);
+              const uint32_t off = (uint32_t)((s0 + 16 * c + i) * 128) + (kc16 ^ (uint32_t)((i & 7) << 4));
+              *reinterpret_cast<uint16_t*>(img + off) = hi;
+              *reinterpret_cast<uint16_t*>(img + off + SLAB) = lo;
+            }
           }
         }
         tc_fence_before();
-        cluster_barrier();                 // the new h of all 128 units is in every CTA's image
-      }
-
-      // ================= classifier on the top layer's h_t: CTA r takes streams [8r, 8r+8) of the tile
-      {
-        const uint8_t* img = base + OFF_AH + (L - 1) * 4 * SLAB;
-        const int per = M / CL;
-        for (int o = warp; o < per * a.odim; o += NT / 32) {
-          const int sl = o / a.odim, j = o - sl * a.odim, ms = per * (int)rank + sl;
-          if (ms >= Mv) continue;
-          const float* wc = vec + a.v_wc + j;            // WcT[k][odim]
-          float acc = 0.f;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.x0_rdy);
+        TSEG_END(s_x0, tx0)
+        // ================= GRU layers
 #pragma unroll
-          for (int u = 0; u < H / 32; ++u) {
-            const int k = lane + 32 * u;
-            const uint32_t off = a_off(ms, k);
-            const float hv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + off)) +
-                             __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + off + SLAB));
-            acc = fmaf(__ldg(wc + k * a.odim), hv, acc);
+        for (int l = 0; l < 2; ++l) {
+          if (l >= L) break;
+          const float* bih = vec + a.v_layers + (size_t)l * a.v_layer_stride + 2 * H * 3 * H;   // b_ih (384) then b_hh (384)
+          const float* bhh = bih + 3 * H;
+          const float nb_r = -LOG2E * (__ldg(bih + j) + __ldg(bhh + j)), nb_z = -LOG2E * (__ldg(bih + H + j) + __ldg(bhh + H + j));
+          const float b_nx = __ldg(bih + 2 * H + j), b_nh = __ldg(bhh + 2 * H + j);
+          if (l == 0) { TWAIT(t_d0, wait_flip(&bars.d_bar[0], p_d0)); } else { TWAIT(t_d1, wait_flip(&bars.d_bar[1], p_d1)); }
+          tc_fence_after();
+          TSEG_BEGIN(tg)
+          const uint32_t td = trow + TM_LAYER * l + s0;
+          uint8_t* img = base + OFF_H + l * IMG + kbase;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c >= nchunk) break;
+            float gr[16], gz[16], gx[16], gh[16];
+            tmem_ld16(td + TM_R + 16 * c, gr);
+            tmem_ld16(td + TM_Z + 16 * c, gz);
+            tmem_ld16(td + TM_NX + 16 * c, gx);
+            tmem_ld16(td + TM_NH + 16 * c, gh);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float r = sigmoid_fast(gr[i], nb_r);
+              const float z = sigmoid_fast(gz[i], nb_z);
+              const float n = tanh_fast(fmaf(r, gh[i] + b_nh, gx[i] + b_nx));
+              const float hn = n + z * (hreg[l][16 * c + i] - n);   // (1 - z) n + z h
+              hreg[l][16 * c + i] = hn;
+              uint16_t hi, lo;
+              split1(hn, hi, lo);
+              const uint32_t off = (uint32_t)((s0 + 16 * c + i) * 128) + (kc16 ^ (uint32_t)((i & 7) << 4));
+              *reinterpret_cast<uint16_t*>(img + off) = hi;
+              *reinterpret_cast<uint16_t*>(img + off + SLAB) = lo;
+            }
           }
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.h_rdy[l]);
+          if (l == 0) { TSEG_END(s_g0, tg) } else { TSEG_END(s_g1, tg) }
+        }
+        // ================= classifier on the top layer's h_t (classifier.py:54-67): one warp per (stream, output)
+        TWAIT(t_cls, wait_flip(&bars.h_rdy[L - 1], p_h));    // every unit of the new top h is in the image
+        TSEG_BEGIN(tc0)
+        {
+          // 8 (stream, output) pairs per warp pass: lanes split k, the 8 reductions run interleaved, then lane i finishes
+          // pair i (bias, activation, store) -- one latency chain per pass instead of one per pair
+          const uint8_t* img = base + OFF_H + (L - 1) * IMG;
+          const int npair = Mv * a.odim;
+          for (int o0 = 8 * warp; o0 < npair; o0 += 64) {
+            float acc[8];
 #pragma unroll
-          for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-          if (lane == 0) {
-            acc += __ldg(vec + a.v_bc + j);
-            if (a.act == WEKWS_ACT_SIGMOID) acc = sigmoidf_acc(acc);
-            a.out[((size_t)(b0 + ms) * T + t) * a.odim + j] = acc;
+            for (int i = 0; i < 8; ++i) {
+              const int o = min(o0 + i, npair - 1);
+              const int ms = a.odim == 1 ? o : o / a.odim, jo = a.odim == 1 ? 0 : o - ms * a.odim;
+              const float* wc = vec + a.v_wc + jo;             // WcT[k][odim]
+              float v = 0.f;
+#pragma unroll
+              for (int u = 0; u < H / 32; ++u) {
+                const int k = lane + 32 * u;
+                const uint32_t off = a_off(ms, k);
+                const float hv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + off)) +
+                                 __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(img + off + SLAB));
+                v = fmaf(__ldg(wc + k * a.odim), hv, v);
+              }
+              acc[i] = v;
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], sft);
+            float mine = acc[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) mine = lane == i ? acc[i] : mine;
+            const int o = o0 + lane;
+            if (lane < 8 && o < npair) {
+              const int ms = a.odim == 1 ? o : o / a.odim, jo = a.odim == 1 ? 0 : o - ms * a.odim;
+              mine += __ldg(vec + a.v_bc + jo);
+              if (a.act == WEKWS_ACT_SIGMOID) mine = sigmoidf_acc(mine);
+              a.out[((size_t)(b0 + ms) * T + t) * a.odim + jo] = mine;
+            }
           }
         }
+        TSEG_END(s_cls, tc0)
       }
-      // the classifier's reads of the top image precede this CTA's next cluster barrier, hence every peer's next
-      // overwrite of it (which sits behind two more barriers)
-    }
-    // ---- final hidden state of my units
-    if (live) {
-      for (int l = 0; l < L; ++l) {
-        float* dst = a.out_cache + ((size_t)l * a.B + b0 + m) * H + UPC * rank;
-        const float* ho = hown + (l * M + m) * UPC;
+      // ---- final hidden state
+      TSEG_BEGIN(tf0)
 #pragma unroll
-        for (int u = 0; u < UPC; u += 4) *reinterpret_cast<float4*>(dst + u) = *reinterpret_cast<const float4*>(ho + u);
+      for (int l = 0; l < 2; ++l) {
+        if (l >= L) break;
+        float* hout = a.out_cache + ((size_t)l * a.B + b0 + s0) * H + j;
+        const int nlive = Mv - s0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nlive) hout[i * H] = hreg[l][i];
       }
+      // the top layer's image is rewritten by the next tile's prologue: every owner must be done with its classifier
+      // reads (named barrier among the 256 owners)
+      TSEG_END(s_fin, tf0)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    cluster_barrier();                     // tile boundary: images are rebuilt for the next tile
+#if GRU_TIMING
+    if (blockIdx.x == 0 && tid == 0)
+      printf("owner: total %lld cycles, waits: lin %lld, d0 %lld, d1 %lld, top-h %lld; busy: prologue %lld, x0 %lld, gates0 %lld, gates1 %lld, classifier %lld, final %lld\n",
+             clock64() - t_begin, t_lin, t_d0, t_d1, t_cls, s_pro, s_x0, s_g0, s_g1, s_cls, s_fin);
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, TM_COLS);
-  cluster_barrier();                       // no CTA leaves while peers may still address its shared memory
+  if (warp == 8) tmem_dealloc(tmem, TM_COLS);
 }
 
 }  // namespace
 
-size_t gru_tc_image_bytes() { return (size_t)CL * (4 * WP_SLAB + 2 * W_LAYER); }
+size_t gru_tc_image_bytes(int L, int idim) { return (size_t)(2 * ((idim + 63) / 64) + 24 * L) * CHUNK; }
 
 bool gru_tc_eligible(int L, int H_, int idim) { return H_ == H && (L == 1 || L == 2) && idim >= 1 && idim <= 96; }
 
-// host: bf16 hi|lo K-major SWIZZLE_128B images of rank r's slices (tc_common.cuh layout: row n at n*128, 16-byte chunk
-// c of a 64-wide K slab at chunk c ^ (n & 7))
+// host: the per-step weight stream, in the order the MMA issuer consumes it.  Every chunk is a K-major SWIZZLE_128B
+// bf16 image of 128 rows (hidden units) x 64 K (tc_common.cuh layout: row n at n*128, 16-byte chunk c of the slab at
+// chunk c ^ (n & 7)); per K slab a hi chunk then a lo chunk.  Order: Linear; per layer W_hh (r, z, n) then W_ih (r, z, n).
 void gru_tc_pack(uint8_t* dst, const float* wp /*[H][idim]*/, int idim, const float* const* wih /*[L] of [3H][H]*/,
                  const float* const* whh, int L, uint16_t (*bf16_rn)(float), float (*bf16_to_f)(uint16_t)) {
-  const size_t per_rank = 4 * WP_SLAB + 2 * W_LAYER;
-  memset(dst, 0, CL * per_rank);
-  auto put = [&](uint8_t* img_hi, uint8_t* img_lo, int n, int kk, float w) {
-    const uint16_t hi = bf16_rn(w), lo = bf16_rn(w - bf16_to_f(hi));
-    const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-    memcpy(img_hi + off, &hi, 2);
-    memcpy(img_lo + off, &lo, 2);
-  };
-  for (int r = 0; r < CL; ++r) {
-    uint8_t* base = dst + (size_t)r * per_rank;
-    for (int n = 0; n < UPC; ++n)                       // preprocessing Linear rows 16r + n
-      for (int k = 0; k < idim; ++k)
-        put(base + (k >> 6) * 2 * WP_SLAB, base + (k >> 6) * 2 * WP_SLAB + WP_SLAB, n, k & 63, wp[(size_t)(UPC * r + n) * idim + k]);
-    for (int l = 0; l < L; ++l)
-      for (int which = 0; which < 2; ++which) {
-        const float* W = which == 0 ? wih[l] : whh[l];
-        uint8_t* wb = base + 4 * WP_SLAB + (size_t)l * W_LAYER + (size_t)which * 4 * W_SLABB;
-        for (int n = 0; n < NG; ++n) {
-          const int row = (n / UPC) * H + UPC * r + (n % UPC);     // gate (r, z, n) x unit
-          for (int k = 0; k < H; ++k)
-            put(wb + (k >> 6) * 2 * W_SLABB, wb + (k >> 6) * 2 * W_SLABB + W_SLABB, n, k & 63, W[(size_t)row * H + k]);
-        }
+  memset(dst, 0, gru_tc_image_bytes(L, idim));
+  uint8_t* p = dst;
+  auto slab = [&](const float* W, int ld, int row0, int k0, int kn) {    // rows row0..row0+127, K k0..k0+kn-1
+    uint8_t* hi_img = p;
+    uint8_t* lo_img = p + CHUNK;
+    for (int n = 0; n < H; ++n)
+      for (int kk = 0; kk < kn; ++kk) {
+        const float w = W[(size_t)(row0 + n) * ld + k0 + kk];
+        const uint16_t hi = bf16_rn(w), lo = bf16_rn(w - bf16_to_f(hi));
+        const size_t off = (size_t)n * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+        memcpy(hi_img + off, &hi, 2);
+        memcpy(lo_img + off, &lo, 2);
       }
+    p += 2 * CHUNK;
+  };
+  for (int s = 0; s * 64 < idim; ++s) slab(wp, idim, 0, 64 * s, idim - 64 * s < 64 ? idim - 64 * s : 64);
+  for (int l = 0; l < L; ++l) {
+    for (int g = 0; g < 3; ++g)
+      for (int s = 0; s < 2; ++s) slab(whh[l], H, g * H, 64 * s, 64);
+    for (int g = 0; g < 3; ++g)
+      for (int s = 0; s < 2; ++s) slab(wih[l], H, g * H, 64 * s, 64);
   }
 }
 
 int gru_tc_launch(GruTcArgs a, cudaStream_t st) {
   WEKWS_REQUIRE(a.B >= 1 && a.T >= 1, "gru_tc_launch: empty call");
-  a.n_tiles = (a.B + M - 1) / M;
+  // streams per tile: fewer streams per CTA shorten the gate math on the critical path of a step (it is SFU-bound: six
+  // ex2 / rcp per unit and stream), the weight stream per CTA and step is the same 786 KB whatever the tile holds
+  const int sms0 = device_sm_count();
+  a.ms = a.B > 32 * sms0 ? 64 : a.B > 16 * sms0 ? 32 : 16;
+  if (const char* e = getenv("WEKWS_GRU_MS")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) a.ms = v; }
+  a.n_tiles = (a.B + a.ms - 1) / a.ms;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -407,9 +565,8 @@ int gru_tc_launch(GruTcArgs a, cudaStream_t st) {
     attr_set[dev] = true;
   }
   const int sms = device_sm_count();
-  int nclusters = a.n_tiles;
-  if (nclusters > sms / CL) nclusters = sms / CL;
-  gru_tc_kernel<<<nclusters * CL, NT, SMEM_BYTES, st>>>(a);
+  const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  gru_tc_kernel<<<grid, NT, SMEM_BYTES, st>>>(a);
   return check_launch("gru_tc_kernel");
 }
 

@@ -110,7 +110,7 @@ struct wekws_model {
   float* d_cbias = nullptr;
   float* d_hidden = nullptr;                // (B, T, 256) scratch between the two kernels; grows monotonically
   size_t hidden_cap = 0;
-  bool gru_tc_ok = false;                   // cluster / tensor-core GRU (gru_tc.cu): images live in h_wimg / d_wimg
+  bool gru_tc_ok = false;                   // tensor-core GRU (gru_tc.cu): weight stream lives in h_wimg / d_wimg
   GruTcArgs grutc{};
 };
 
@@ -471,7 +471,7 @@ int pack_gru(wekws_model* m) {
   }
   if ((rc = pack_classifier(m, H, &a.v_wc, &a.v_bc))) return rc;
   a.L = L; a.H = H; a.idim = idim; a.odim = c.odim; a.act = c.activation; a.has_cmvn = m->has_cmvn ? 1 : 0;
-  // cluster / tensor-core variant: per-rank operand images of the hidden-unit slices
+  // tensor-core variant: the per-step weight stream as pre-swizzled bf16 hi|lo operand chunks
   m->gru_tc_ok = false;
   m->h_wimg.clear();
   if (gru_tc_eligible(L, H, idim)) {
@@ -482,7 +482,7 @@ int pack_gru(wekws_model* m) {
       if ((rc = get_tensor(m, "backbone.weight_ih" + sfx, (size_t)G * H, &wih[l]))) return rc;
       if ((rc = get_tensor(m, "backbone.weight_hh" + sfx, (size_t)G * H, &whh[l]))) return rc;
     }
-    m->h_wimg.assign(gru_tc_image_bytes(), 0);
+    m->h_wimg.assign(gru_tc_image_bytes(L, idim), 0);
     gru_tc_pack(m->h_wimg.data(), wp, idim, wih, whh, L, bf16_rn, bf16_to_f);
     GruTcArgs& t = m->grutc;
     memset(&t, 0, sizeof(t));
@@ -680,14 +680,28 @@ extern "C" int wekws_model_finalize(wekws_model* m) {
 }
 
 extern "C" int wekws_model_set_precision(wekws_model* m, int mode) {
-  WEKWS_REQUIRE(m && (mode == 0 || mode == 1), "wekws_model_set_precision: mode must be 0 (auto) or 1 (fp32)");
+  WEKWS_REQUIRE(m && mode >= 0 && mode <= 2, "wekws_model_set_precision: mode must be 0 (auto), 1 (fp32) or 2 (tensor cores wherever a kernel exists)");
   m->precision = mode;
   return WEKWS_OK;
 }
 
+// GRU: which kernel is faster depends on the batch as well (measured on B200, scripts/gru_sweep.py): the weight-streaming
+// tensor-core kernel takes ~9-10 us per step whatever the batch (up to 148 x 64 streams), the FP32 kernel scales with
+// the streams per SM and has the shorter single-step latency at small batches.
+static bool gru_takes_tc(const wekws_model* m, int64_t B, int64_t T) {
+  if (!m->gru_tc_ok || m->precision == 1 || T < 1) return false;
+  if (m->precision == 2) return true;
+  return B >= (T == 1 ? 640 : T < 8 ? 400 : 256);
+}
+
+extern "C" int wekws_model_uses_tensor_cores_bt(const wekws_model* m, int64_t B, int64_t T) {
+  if (!m || !m->finalized) return 0;
+  if (m->cfg.backbone == WEKWS_BACKBONE_GRU) return gru_takes_tc(m, B, T) ? 1 : 0;
+  return ((m->tc_ok || m->tcn_ok || m->ds_ok) && m->precision != 1 && T >= 8) ? 1 : 0;
+}
+
 extern "C" int wekws_model_uses_tensor_cores(const wekws_model* m, int64_t T) {
-  if (m && m->finalized && m->gru_tc_ok && m->precision == 0 && T >= 1) return 1;
-  return (m && m->finalized && (m->tc_ok || m->tcn_ok || m->ds_ok) && m->precision == 0 && T >= 8) ? 1 : 0;
+  return wekws_model_uses_tensor_cores_bt(m, 1 << 20, T);     // "for a large batch"
 }
 
 extern "C" int64_t wekws_model_packed_floats(const wekws_model* m, int which) {
@@ -739,7 +753,7 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
       int rc = fsmn_launch(a, st);
       if (rc) return rc;
     }
-  } else if (m->cfg.backbone == WEKWS_BACKBONE_GRU && m->gru_tc_ok && m->precision == 0) {
+  } else if (m->cfg.backbone == WEKWS_BACKBONE_GRU && gru_takes_tc(m, B, T)) {
     GruTcArgs a = m->grutc;
     a.feats = d_feats; a.in_cache = d_in_cache; a.out = d_out; a.out_cache = d_out_cache;
     a.B = (int)B; a.T = (int)T;
@@ -755,11 +769,11 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
     // time-chunk long inputs; the cache carries the state between chunks exactly as in
     // streaming use (chunked == full utterance, SURVEY.md 8a "Numerical facts")
     // tensor-core path: mdtc hidden 64, chunks of >= 8 frames, 16-byte aligned cache rows
-    const bool use_tc = m->tc_ok && m->precision == 0 && T >= 8 &&
+    const bool use_tc = m->tc_ok && m->precision != 1 && T >= 8 &&
                         (d_in_cache == nullptr || ((uintptr_t)d_in_cache & 15) == 0) &&
                         ((uintptr_t)d_feats & 15) == 0 && ((uintptr_t)d_out_cache & 15) == 0;
-    const bool use_tcn = m->tcn_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
-    const bool use_ds = m->ds_ok && m->precision == 0 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
+    const bool use_tcn = m->tcn_ok && m->precision != 1 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
+    const bool use_ds = m->ds_ok && m->precision != 1 && T >= 8 && ((uintptr_t)d_feats & 15) == 0;
     const int maxT = use_tc ? tc_max_T() : use_tcn ? tcn_tc_max_T() : use_ds ? dstcn_tc_max_T() : m->conv_max_T;
     if (use_ds && m->cls_tc) {      // hidden scratch between the backbone kernel and the classifier GEMM
       const size_t need = (size_t)B * (size_t)T * (size_t)m->cfg.hdim;
@@ -830,7 +844,7 @@ extern "C" int wekws_model_forward(wekws_model* m, const float* d_feats, const f
       if (rc) return rc;
     }
   }
-  if (m->cfg.backbone == WEKWS_BACKBONE_DSTCN && m->cls_tc && m->ds_ok && m->precision == 0 && T >= 8 &&
+  if (m->cfg.backbone == WEKWS_BACKBONE_DSTCN && m->cls_tc && m->ds_ok && m->precision != 1 && T >= 8 &&
       ((uintptr_t)d_feats & 15) == 0) {
     // classifier (+ activation) of all B*T frames in one tensor-core GEMM over the hidden scratch (classifier.py:63-67)
     LinearTcArgs a;

@@ -184,6 +184,25 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp.  MMA issue loops should be executed by the WHOLE warp with only the instruction itself
+// under `if (elect_one_sync())`: the descriptors are then computed in uniform registers and every tcgen05.mma is a single
+// instruction.  With `if (lane == 0)` around a loop that derives descriptors from values the compiler cannot prove
+// warp-uniform (function arguments, shared-memory loads), every MMA is wrapped in an ELECT / R2UR waterfall loop and one
+// M128 N64 K16 dispatch costs ~105 cycles instead of ~55 (tests/native/mma_rate_probe.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp-uniform copy of a value every lane holds (lets the compiler keep what is derived from it in uniform registers)
+__device__ __forceinline__ uint32_t uniform32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -270,11 +270,25 @@ class KWSModel(nn.Module):
             self.__dict__["_packed_fp"] = self._fingerprint()
         return self._handle
 
-    def uses_tensor_cores(self, T: int) -> bool:
-        '''True if a forward with T frames per call takes the tcgen05 kernel (model already on a GPU).'''
-        if self._handle is None or self._dirty:
+    def uses_tensor_cores(self, T: int, B: int = None) -> bool:
+        '''True if a forward with T frames per call (and, for the GRU, B streams) takes the tcgen05 kernel (model
+        already on a GPU).  Without B the answer is for a large batch.'''
+        if self._handle is None or self._dirty or self.precision == "fp32":
             return False
-        return bool(_native.lib().wekws_model_uses_tensor_cores(self._handle, T)) and self.precision == "auto"
+        self._apply_precision(self._handle)
+        if B is None:
+            return bool(_native.lib().wekws_model_uses_tensor_cores(self._handle, T))
+        return bool(_native.lib().wekws_model_uses_tensor_cores_bt(self._handle, B, T))
+
+    _PRECISIONS = {"auto": 0, "fp32": 1, "tensor": 2}
+
+    def _apply_precision(self, h):
+        if self._precision_applied != self.precision:
+            if self.precision not in self._PRECISIONS:
+                raise ValueError("precision must be 'auto', 'fp32' or 'tensor'")
+            _native.check(_native.lib().wekws_model_set_precision(h, self._PRECISIONS[self.precision]),
+                          "wekws_model_set_precision")
+            self._precision_applied = self.precision
 
 
     # ------------------------------------------------------------------------- forward
@@ -308,12 +322,7 @@ class KWSModel(nn.Module):
                 in_cache = in_cache.to(device=dev, dtype=torch.float32).contiguous()
             cache_ptr = in_cache.data_ptr()
         h = self._ensure(dev)
-        if self._precision_applied != self.precision:
-            if self.precision not in ("auto", "fp32"):
-                raise ValueError("precision must be 'auto' or 'fp32'")
-            _native.check(_native.lib().wekws_model_set_precision(h, 0 if self.precision == "auto" else 1),
-                          "wekws_model_set_precision")
-            self._precision_applied = self.precision
+        self._apply_precision(h)
         out = torch.empty((B, T, self.odim), device=dev, dtype=torch.float32)
         if T == 0 and cache_ptr is not None:
             out_cache = in_cache.clone()
