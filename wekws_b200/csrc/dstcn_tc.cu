@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = uniform32(tmem_slot);      // warp-uniform: MMA operands are then built in uniform registers
   uint32_t mma_par = 0, coef_par = 0;
   const uint32_t idesc = make_idesc_bf16(128, 128);
   const int natoms = (a.idim + 63) / 64;
@@ -123,20 +123,22 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
   auto load_next = [&]() {
     if (gl >= gtotal) return;
     const uint32_t slot = gl % NW, n = gl % (uint32_t)nitems;
-    mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
-    bulk_g2s(Wring + slot * W_SLOT, a.wimg + (size_t)n * W_SLOT, W_SLOT, &w_bar[slot]);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
+      bulk_g2s(Wring + slot * W_SLOT, a.wimg + (size_t)n * W_SLOT, W_SLOT, &w_bar[slot]);
+    }
     ++gl;
   };
   // the cache of the streams of a pass is pulled into L2 one pass ahead, so the depthwise taps that read it
   // straight from global memory see L2 latency instead of HBM latency
   auto prefetch_cache = [&](int first, int n) {
-    if (!a.prefetch_ok) return;
+    if (!a.prefetch_ok || lane != 0) return;
     for (int i = 0; i < n; ++i)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.in_cache + (size_t)(first + i) * C * P),
                    "r"(C * P * 4)
                    : "memory");
   };
-  if (is_issuer && lane == 0) {
+  if (is_issuer) {                                   // whole warp: uniform bookkeeping, lane 0 issues the copies
     for (int i = 0; i < NW; ++i) load_next();
     prefetch_cache(sb, min(spt, se - sb));
   }
@@ -150,18 +152,23 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
     const int rows = ns * T;
 
     if (is_issuer) {
-      // ================================================================== MMA-ISSUE WARP (lane 0 works)
-      if (lane == 0) {
+      // ================================================================== MMA-ISSUE WARP
+      // All lanes run the (uniform) control flow and descriptor arithmetic; the tcgen05 / bulk-copy instructions are
+      // elected.  With `if (lane == 0)` around the whole role every MMA sat in an ELECT / R2UR waterfall loop.
+      {
         // D[:, d_col .. d_col+128) (+)= A(tmem a_hi / a_lo, ksteps K-steps) x W(next image)   -- bf16x3
         auto use_item = [&](uint32_t d_col, uint32_t a_hi, uint32_t a_lo, int ksteps, uint32_t& acc) {
           const uint32_t slot = gu % NW;
           mbar_wait(&w_bar[slot], (gu / NW) & 1);
           const uint64_t dwh = make_sdesc_sw128(smem_u32(Wring + slot * W_SLOT)), dwl = dwh + (16384 >> 4);
           const uint32_t d = tmem + d_col, ahi = tmem + a_hi, alo = tmem + a_lo;
-          for (int k = 0; k < ksteps; ++k) { umma_bf16_ts(d, ahi + 8 * k, dwh + 2 * k, idesc, acc); acc = 1; }
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, alo + 8 * k, dwh + 2 * k, idesc, 1);
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dwl + 2 * k, idesc, 1);
-          umma_commit(&w_free[slot]);
+          if (elect_one_sync()) {
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dwh + 2 * k, idesc, k == 0 ? acc : 1u);
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, alo + 8 * k, dwh + 2 * k, idesc, 1);
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dwl + 2 * k, idesc, 1);
+            umma_commit(&w_free[slot]);
+          }
+          acc = 1;
           if (gu >= 1) {                              // the previous image's MMAs are (nearly) done: refill its slot
             mbar_wait(&w_free[(gu - 1) % NW], ((gu - 1) / NW) & 1);
             load_next();
@@ -174,9 +181,11 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
           tc_fence_after();
         };
         auto load_coef = [&](int blk) {
-          fence_proxy_async();                        // the area was read/written through the generic proxy
-          mbar_arrive_expect_tx(&coef_bar, COEF_FLOATS * 4);
-          bulk_g2s(coef, vec + a.v_blocks + (size_t)blk * a.v_blk_stride, COEF_FLOATS * 4, &coef_bar);
+          if (lane == 0) {
+            fence_proxy_async();                      // the area was read/written through the generic proxy
+            mbar_arrive_expect_tx(&coef_bar, COEF_FLOATS * 4);
+            bulk_g2s(coef, vec + a.v_blocks + (size_t)blk * a.v_blk_stride, COEF_FLOATS * 4, &coef_bar);
+          }
         };
         load_coef(0);
         if (done < se) prefetch_cache(done, min(spt, se - done));
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
             use_item(0, TM_A + 32, TM_A + 96, ks1, acc0);
             use_item(128, TM_A + 32, TM_A + 96, ks1, acc1);
           }
-          umma_commit(&mma_bar);
+          if (elect_one_sync()) umma_commit(&mma_bar);
         }
         // ---- blocks: K slab ks of block blk
         for (int blk = 0; blk < a.nblocks; ++blk) {
@@ -205,8 +214,10 @@ __global__ void __launch_bounds__(NT_TC, 1) dstcn_tc_kernel(const DsTcArgs a) {
             uint32_t acc0 = ks > 0 ? 1u : 0u, acc1 = acc0;
             use_item(0, TM_A + 64 * b, TM_A + 32 + 64 * b, 4, acc0);
             use_item(128, TM_A + 64 * b, TM_A + 32 + 64 * b, 4, acc1);
-            umma_commit(&ab_free[b]);
-            if (ks == 3) umma_commit(&mma_bar);
+            if (elect_one_sync()) {
+              umma_commit(&ab_free[b]);
+              if (ks == 3) umma_commit(&mma_bar);
+            }
           }
         }
         wd_mark(3000);

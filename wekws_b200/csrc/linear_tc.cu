@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const LinearTcArgs a) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = uniform32(tmem_slot);      // warp-uniform: MMA operands are then built in uniform registers
   const int nslab = a.K / 64, ntn = (a.N + NTILE - 1) / NTILE;
   const int my_tiles = a.n_mtiles > (int)blockIdx.x ? (a.n_mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t idesc = make_idesc_bf16(128, NTILE);
@@ -129,8 +129,9 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const LinearTcArgs a) 
       }
     }
   } else if (warp == 4) {
-    // ================================================================== MMA ISSUER (lane 0)
-    if (lane == 0) {
+    // ================================================================== MMA ISSUER (whole warp, tcgen05 instructions elected:
+    // uniform values keep the descriptors in uniform registers, see tc_common.cuh elect_one_sync)
+    {
       uint32_t seq = 0, ardy_par = 0, dfree_par = 0, used[2] = {0, 0};
       for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(&a_rdy, ardy_par);
@@ -152,14 +153,17 @@ __global__ void __launch_bounds__(NT, 1) linear_tc_kernel(const LinearTcArgs a) 
             tc_fence_after();
             const uint64_t whi = make_sdesc_sw128(smem_u32(base + slot * W_SLOT)), wlo = make_sdesc_sw128(smem_u32(base + slot * W_SLOT) + 16384);
             const uint32_t ahi = tmem + TM_AHI + 32 * s, alo = tmem + TM_ALO + 32 * s;
-            for (int k = 0; k < 4; ++k) { umma_bf16_ts(d, ahi + 8 * k, whi + 2 * k, idesc, acc); acc = 1; }
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(d, alo + 8 * k, whi + 2 * k, idesc, 1);
-            for (int k = 0; k < 4; ++k) umma_bf16_ts(d, ahi + 8 * k, wlo + 2 * k, idesc, 1);
-            umma_commit(&w_free[slot]);
+            if (elect_one_sync()) {
+              for (int k = 0; k < 4; ++k) umma_bf16_ts(d, ahi + 8 * k, whi + 2 * k, idesc, k == 0 ? acc : 1u);
+              for (int k = 0; k < 4; ++k) umma_bf16_ts(d, alo + 8 * k, whi + 2 * k, idesc, 1);
+              for (int k = 0; k < 4; ++k) umma_bf16_ts(d, ahi + 8 * k, wlo + 2 * k, idesc, 1);
+              umma_commit(&w_free[slot]);
+            }
+            acc = 1;
           }
-          umma_commit(&d_full[buf]);
+          if (elect_one_sync()) umma_commit(&d_full[buf]);
         }
-        umma_commit(&a_free);
+        if (elect_one_sync()) umma_commit(&a_free);
       }
     }
   } else {

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = uniform32(tmem_slot);        // warp-uniform: MMA operands are then built in uniform registers
   const Bars bars{mma_bar, halo_bar, a_rdy, h_free, w_bar, w_free, vec_bar, stg_bar};
   // phase parities: every waiter keeps its own copy; all copies of a barrier advance in lock step
   uint32_t mma_par = 0, halo_par = 0, ar_par = 0, vec_par = 0, tok_par = 0;   // compute groups
@@ -298,18 +298,22 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           mbar_wait(&a_rdy[grp], ar_par);
           ar_par ^= 1;
           tc_fence_after();
-          if (lane == 0) {
-            if (job < 0) {
-              mbar_wait(&w_bar[0], w_par & 1);
-              if (natoms > 1) mbar_wait(&w_bar[1], (w_par >> 1) & 1);
+          // the whole warp runs the issue path (uniform values -> descriptors in uniform registers, every MMA a single
+          // instruction); only the tcgen05 instructions themselves are elected
+          if (job < 0) {
+            mbar_wait(&w_bar[0], w_par & 1);
+            if (natoms > 1) mbar_wait(&w_bar[1], (w_par >> 1) & 1);
+            if (elect_one_sync()) {
               uint32_t acc = 0;
               issue_gemm(0, 0, (min(a.idim, 64) + 15) >> 4, acc);
               if (natoms > 1) issue_gemm(32, 1, (a.idim - 64 + 15) >> 4, acc);
               umma_commit(&mma_bar[grp]);
               umma_commit(&w_free[0]);
               if (natoms > 1) umma_commit(&w_free[1]);
-            } else {
-              mbar_wait(&w_bar[job], (w_par >> job) & 1);
+            }
+          } else {
+            mbar_wait(&w_bar[job], (w_par >> job) & 1);
+            if (elect_one_sync()) {
               uint32_t acc = 0;
               issue_gemm(0, job, 4, acc);
               umma_commit(&mma_bar[grp]);
@@ -582,17 +586,21 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             }
           }
         }
-      } else if (wq == 0 && lane == 0) {
-        // a group without streams in this pass still releases every weight slot use (w_free counts NG arrivals)
+      } else if (wq == 0) {
+        // a group without streams in this pass still releases every weight slot use (w_free counts NG arrivals); all
+        // lanes keep the same phase bookkeeping
         mbar_wait(&w_bar[0], w_par & 1);
-        mbar_arrive(&w_free[0]);
-        if (natoms > 1) { mbar_wait(&w_bar[1], (w_par >> 1) & 1); mbar_arrive(&w_free[1]); }
+        if (lane == 0) mbar_arrive(&w_free[0]);
+        if (natoms > 1) {
+          mbar_wait(&w_bar[1], (w_par >> 1) & 1);
+          if (lane == 0) mbar_arrive(&w_free[1]);
+        }
         w_par ^= natoms > 1 ? 3u : 1u;
         for (int blk = 0; blk < a.nblocks; ++blk)
           for (int job = 0; job < 2; ++job) {
             mbar_wait(&w_bar[job], (w_par >> job) & 1);
             w_par ^= 1u << job;
-            mbar_arrive(&w_free[job]);
+            if (lane == 0) mbar_arrive(&w_free[job]);
           }
       }
     } else if (warp == W_WGT) {

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = uniform32(tmem_slot);      // warp-uniform: MMA operands are then built in uniform registers
   uint32_t mma_par = 0, halo_par = 0, ar_par = 0, hf_par = 0;
   uint32_t witem = 0;                              // issuer: weight items consumed so far (slot = item % NW)
   uint32_t ab_cnt[NTILE][2] = {{0, 0}, {0, 0}};     // compute: commits of ab_free[i][b] before the current block
@@ -110,13 +110,17 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
     auto tile_streams = [&](int i) { return min(spt, ns - i * spt); };
 
     if (is_issuer) {
-      // ================================================================== MMA-ISSUE WARP (lane 0 works)
-      if (lane == 0) {
+      // ================================================================== MMA-ISSUE WARP
+      // All lanes run the (uniform) control flow and descriptor arithmetic; the tcgen05 / bulk-copy instructions are
+      // elected.  With `if (lane == 0)` around the whole role every MMA sat in an ELECT / R2UR waterfall loop.
+      {
         int loaded = 0, freed = 0;                   // items whose load was issued / whose slot was reclaimed
         auto load_item = [&](int n) {                // item n of this pass -> its ring slot
           const uint32_t slot = (witem + (uint32_t)n) % NW;
-          mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
-          bulk_g2s(Wring + slot * W_SLOT, a.wimg + (size_t)n * W_SLOT, W_SLOT, &w_bar[slot]);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&w_bar[slot], W_SLOT);
+            bulk_g2s(Wring + slot * W_SLOT, a.wimg + (size_t)n * W_SLOT, W_SLOT, &w_bar[slot]);
+          }
         };
         auto reclaim = [&](int n) {                  // wait until the MMAs that read item n are done, then refill
           const uint32_t use = witem + (uint32_t)n, slot = use % NW;
@@ -128,13 +132,16 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
           mbar_wait(&w_bar[slot], (use / NW) & 1);
           return make_sdesc_sw128(smem_u32(Wring + slot * W_SLOT));
         };
-        auto release_w = [&](int n) { umma_commit(&w_free[(witem + (uint32_t)n) % NW]); };
+        auto release_w = [&](int n) { if (elect_one_sync()) umma_commit(&w_free[(witem + (uint32_t)n) % NW]); };
         auto issue_gemm = [&](int i, int a_hi_col, int a_lo_col, uint64_t dwh, int ksteps, uint32_t& acc) {
           const uint32_t d = tmem + TM_TILE * i, ahi = d + a_hi_col, alo = d + a_lo_col;
           const uint64_t dwl = dwh + (8192 >> 4);
-          for (int k = 0; k < ksteps; ++k) { umma_bf16_ts(d, ahi + 8 * k, dwh + 2 * k, idesc, acc); acc = 1; }
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, alo + 8 * k, dwh + 2 * k, idesc, 1);
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dwl + 2 * k, idesc, 1);
+          if (elect_one_sync()) {
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dwh + 2 * k, idesc, k == 0 ? acc : 1u);
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, alo + 8 * k, dwh + 2 * k, idesc, 1);
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(d, ahi + 8 * k, dwl + 2 * k, idesc, 1);
+          }
+          acc = 1;
         };
         // one hand-over barrier per operand buffer: with a single one the compute warps could complete the phase
         // of tap j+1 before this thread had observed the phase of tap j (their only back-pressure is ab_free of
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
           uint32_t acc = 0;
           issue_gemm(i, 64, 128, dwp0, ks0, acc);
           if (natoms > 1) issue_gemm(i, 64 + 32, 128 + 32, dwp1, ks1, acc);
-          umma_commit(&mma_bar[i]);
+          if (elect_one_sync()) umma_commit(&mma_bar[i]);
         }
         release_w(0); release_w(1);
         // ---- blocks: tap j of block blk is item 2 + blk*K + j
@@ -171,8 +178,10 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
               wd_mark(2000000 + n * 10 + i);
               uint32_t acc = j > 0 ? 1u : 0u;
               issue_gemm(i, 64 + 64 * (j & 1), 96 + 64 * (j & 1), dwh, 4, acc);
-              umma_commit(&ab_free[i][j & 1]);
-              if (j == K - 1) umma_commit(&mma_bar[i]);
+              if (elect_one_sync()) {
+                umma_commit(&ab_free[i][j & 1]);
+                if (j == K - 1) umma_commit(&mma_bar[i]);
+              }
             }
             release_w(n);
           }
