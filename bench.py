@@ -480,8 +480,8 @@ class Runner:
                     traffic = json.load(f).get(workload, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        tc = bool(model.uses_tensor_cores(T))
-        kname = "gru_kernel" if gru else ({"tcn": "tcn_tc_kernel", "ds_tcn": "dstcn_tc_kernel"}.get(
+        tc = bool(model.uses_tensor_cores(T, B))
+        kname = ("gru_tc_kernel" if tc else "gru_kernel") if gru else ({"tcn": "tcn_tc_kernel", "ds_tcn": "dstcn_tc_kernel"}.get(
             model_name, "mdtc_tc_kernel") if tc else "conv_backbone_kernel")
         flop_per_frame = {"mdtc": 299776, "tcn": 272512, "ds_tcn": 582144, "gru": 413952}.get(model_name)
         res = {
