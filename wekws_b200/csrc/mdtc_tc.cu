@@ -31,6 +31,16 @@
 #include "mdtc_tc.h"
 #include "tc_common.cuh"
 
+// per-phase cycle counters of a few warps (debug builds with -DMDTC_TIMING=1 only; see profiles/r02_mdtc_notes.md)
+#ifndef MDTC_TIMING
+#define MDTC_TIMING 0
+#endif
+#if MDTC_TIMING
+#define TPH(acc) { const long long t_now_ = clock64(); acc += t_now_ - t_last_; t_last_ = t_now_; }
+#else
+#define TPH(acc)
+#endif
+
 namespace wekws {
 
 namespace {
@@ -143,20 +153,61 @@ __device__ __noinline__ void loader_role(const TcArgs& a, uint8_t* base, Bars B,
     mbar_arrive_expect_tx(&B.stg_bar[slot], (uint32_t)(C * pad * 4));
     tma_load_2d(STG + slot * STG_FLOATS, &a.tmap[a.tmap_idx[blk]], a.coff[blk], (b0 + sg) * C, &B.stg_bar[slot]);
   };
+  // (an up-front cp.async.bulk.prefetch.L2 of the streams' whole cache rows was measured: 3 % slower)
   if (have_cache && lane == 0)
     for (int k0 = 0; k0 < nsl && k0 < njobs; ++k0) issue_tma(k0);
   int k = 0;
+#if MDTC_TIMING
+  long long t_hf = 0, t_stg = 0, t_tr = 0;
+  long long t_last_ = clock64();
+#endif
   for (int blk = 0; blk < a.nblocks; ++blk) {
     const int pad = a.dil[blk] * (K - 1);
-    // lane -> (column j of the slice, channel-quad sub-index): four loads down the slot's channel rows, one
-    // STS.128 = 4 channels of one column of X
-    const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
-    const int j = lane & (jpl - 1), qs = lane >> lgj;
-    // X's pad columns of the tile are free once DW + cache stores (blk-1) are done (at blk 0: from the start)
+    // X's pad columns of the tile are free once the depthwise conv of blk-1 is done (at blk 0: from the start)
     if (blk > 0) {
       if (lane == 0) mbar_wait_backoff(&B.h_free[i], hf_par & 1);
       hf_par ^= 1u;
       __syncwarp();
+    }
+    TPH(t_hf)
+    // one 4-channel x 4-column item: four LDS.128 along the slot's (time-minor) channel rows, a register transpose,
+    // four STS.128 (4 channels of one column each) -- 8 shared-memory instructions per 64 bytes
+    const int lgg = 31 - __clz(pad >> 2);          // column groups of 4 per channel row (pad is a power of two >= 4)
+    auto move_item = [&](const float* slotp, int colb, int r) {
+      const int cq = r >> lgg, jg = r & ((1 << lgg) - 1);
+      const float4* s4 = reinterpret_cast<const float4*>(slotp + 4 * cq * pad + 4 * jg);
+      const float4 r0 = s4[0], r1 = s4[pad >> 2], r2 = s4[2 * (pad >> 2)], r3 = s4[3 * (pad >> 2)];
+      const uint32_t sw = ((uint32_t)(cq >> 1) << 4), hi = (uint32_t)(cq & 1) * 128u;
+      uint32_t col = (uint32_t)(colb + 4 * jg);
+      sts_2x2(((xs + (col << 8) + ((col & 7u) << 4)) ^ sw) + hi, pack2(r0.x, r1.x), pack2(r2.x, r3.x)); ++col;
+      sts_2x2(((xs + (col << 8) + ((col & 7u) << 4)) ^ sw) + hi, pack2(r0.y, r1.y), pack2(r2.y, r3.y)); ++col;
+      sts_2x2(((xs + (col << 8) + ((col & 7u) << 4)) ^ sw) + hi, pack2(r0.z, r1.z), pack2(r2.z, r3.z)); ++col;
+      sts_2x2(((xs + (col << 8) + ((col & 7u) << 4)) ^ sw) + hi, pack2(r0.w, r1.w), pack2(r2.w, r3.w));
+    };
+    if (have_cache && nsl >= nst) {
+      // every stream of the tile has its own landing slot: wait for all of them (they were requested a block ago), move
+      // everything in ONE flat loop, signal the group, and only then recycle the slots -- one latency chain per block
+      // instead of one per stream (the per-stream version kept the group waiting on halo_bar 10-17 % of the time)
+      for (int m = 0; m < nst; ++m) {
+        const uint32_t use = (uint32_t)(k + m);
+        mbar_wait(&B.stg_bar[slot0 + use % nsl], (use / nsl) & 1);
+      }
+      TPH(t_stg)
+      const int per = 16 << lgg;
+      for (int it = lane; it < nst * per; it += 32) {
+        const int m = it >> (4 + lgg);
+        move_item(STG + (slot0 + (uint32_t)(k + m) % nsl) * STG_FLOATS, (sg0 + m) * Lw + PADR - pad, it & (per - 1));
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&B.halo_bar[i]);               // the tile's slices of this block are in place
+        fence_proxy_async();                       // the slots were read through the generic proxy; TMA rewrites them
+        for (int m = 0; m < nst; ++m)
+          if (k + m + nsl < njobs) issue_tma(k + m + nsl);
+      }
+      k += nst;
+      TPH(t_tr)
+      continue;
     }
     for (int sg = sg0; sg < sg0 + nst; ++sg, ++k) {
       const int colb = sg * Lw + PADR - pad;       // first cache column of this stream for this block
@@ -164,15 +215,8 @@ __device__ __noinline__ void loader_role(const TcArgs& a, uint8_t* base, Bars B,
         const uint32_t use = (uint32_t)k, slot = slot0 + use % nsl;
         if (lane == 0) mbar_wait_backoff(&B.stg_bar[slot], (use / nsl) & 1);
         __syncwarp();
-        const float* src = STG + slot * STG_FLOATS + j;
-        const uint32_t col = (uint32_t)(colb + j);
-        const uint32_t tcol = xs + (col << 8) + ((col & 7u) << 4);
-#pragma unroll 4
-        for (int cq = qs; cq < 16; cq += qstep) {
-          const float* s4 = src + 4 * cq * pad;
-          const float a0 = s4[0], a1 = s4[pad], a2 = s4[2 * pad], a3 = s4[3 * pad];
-          sts_2x2((tcol ^ ((uint32_t)(cq >> 1) << 4)) + (uint32_t)(cq & 1) * 128u, pack2(a0, a1), pack2(a2, a3));
-        }
+        const float* slotp = STG + slot * STG_FLOATS;
+        for (int it = lane; it < (16 << lgg); it += 32) move_item(slotp, colb, it);
         __syncwarp();                              // every lane has read the slot
         if (lane == 0 && k + nsl < njobs) {        // refill it: the same ring position, nsl jobs ahead
           fence_proxy_async();                     // the slot was read through the generic proxy; TMA rewrites it
@@ -185,7 +229,11 @@ __device__ __noinline__ void loader_role(const TcArgs& a, uint8_t* base, Bars B,
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&B.halo_bar[i]);    // the tile's slices of this block are in place
+    TPH(t_tr)
   }
+#if MDTC_TIMING
+  if (blockIdx.x == 0 && lane == 0) printf("loader %d: wait h_free %lld, wait landing %lld, transposes %lld (nsl %d)\n", i, t_hf, t_stg, t_tr, nsl);
+#endif
   // DW of the last block still signals h_free: consume it so the parity stays in step
   if (lane == 0) mbar_wait_backoff(&B.h_free[i], hf_par & 1);
   hf_par ^= 1u;
@@ -381,6 +429,11 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         group_barrier(grp);                  // X of the tile complete before the first depthwise conv reads across rows
 
         // ---- blocks
+#if MDTC_TIMING
+        long long t_halo = 0, t_dw = 0, t_ho0 = 0, t_cs = 0, t_w1 = 0, t_e1 = 0, t_ho1 = 0, t_w2 = 0, t_e2 = 0, t_gb = 0;
+        long long t_last_ = clock64();
+        const long long t_blocks0 = t_last_;
+#endif
         for (int blk = 0; blk < a.nblocks; ++blk) {
           const int d = a.dil[blk], pad = d * (K - 1);
           const uint32_t vb = vsm + (uint32_t)blk * (VEC_FLOATS * 4);
@@ -392,6 +445,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           }
           mbar_wait(&halo_bar[grp], halo_par);
           halo_par ^= 1;
+          TPH(t_halo)
           // The depthwise conv is the shared-memory-bandwidth phase (22 LDS.128 per 8 channels) while the epilogues and
           // the GEMM waits leave the load/store pipe idle.  Groups that run in lock step all hit it at once and then all
           // idle; a token handed from group to group (g -> g + 1 -> ... -> 0 of the next block) keeps exactly one
@@ -442,7 +496,15 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&dw_tok[grp + 1 == ntile ? 0 : grp + 1]);
           }
+          // this warp is done with the block's cache columns in front of the frames: when the new cache slice is made of
+          // frame columns only (T >= pad) the loader may start transposing the next block's slices now, not after the
+          // stores below (which read those columns when T < pad)
+          const bool early_free = T >= pad;
+          __syncwarp();
+          if (early_free && lane == 0) mbar_arrive(&h_free[grp]);
+          TPH(t_dw)
           hand_over(0);
+          TPH(t_ho0)
           // ---------------- new cache slices of this tile while its pointwise-1 GEMM runs:
           // out_cache[b][c][off + j] = cat[c][T + j] (mdtc.py:113).  A warp reads 8 columns x 4 channels per request
           // (conflict-free in the swizzled layout); 8 lanes write 32 contiguous bytes of one cache row.
@@ -466,12 +528,16 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               float* g = a.out_cache + ((size_t)(b0 + sg2) * C + 4 * cq) * a.P + off + j;
               g[0] = v0; g[a.P] = v1; g[2 * a.P] = v2; g[3 * a.P] = v3;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_free[grp]);      // the tile's cache columns may be overwritten
+            if (!early_free) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&h_free[grp]);    // the tile's cache columns may be overwritten
+            }
           }
           // ---------------- h = relu(D + b1) -> operand rows in TMEM                          (mdtc.py:115)
           // (16 accumulator columns at a time: this thread's 32 channels in two rounds, 72 registers per thread)
+          TPH(t_cs)
           wait_mma();
+          TPH(t_w1)
           if (q_live) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -493,9 +559,12 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               tmem_st8(tm_row + TM_ALO + 16 * g + 8 * hh, l);
             }
           }
+          TPH(t_e1)
           hand_over(1);
+          TPH(t_ho1)
           // ---------------- x' = relu(D + b2 + x) -> X; classifier partial sums at the end of a stack
           wait_mma();                                                          // (mdtc.py:116-118, 266-273)
+          TPH(t_w2)
           if (q_live) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -549,9 +618,16 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
               }
             }
           }
+          TPH(t_e2)
           tc_fence_before();
           group_barrier(grp);                // x' of every row of the tile complete before the next block's conv
+          TPH(t_gb)
         }
+#if MDTC_TIMING
+        if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5 || warp == 8 || warp == 16))
+          printf("warp %2d: blocks %lld cycles | halo %lld dw %lld handover0 %lld cache-store %lld wait1 %lld epi1 %lld handover1 %lld wait2 %lld epi2 %lld barrier %lld\n",
+                 warp, clock64() - t_blocks0, t_halo, t_dw, t_ho0, t_cs, t_w1, t_e1, t_ho1, t_w2, t_e2, t_gb);
+#endif
 
         if (ntile > 1 && (a.debug & 1) && grp == 0) {    // the last group's final hand-off: keep the parities in step
           mbar_wait(&dw_tok[0], tok_par);
