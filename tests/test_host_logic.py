@@ -188,6 +188,54 @@ def test_tensor_core_weight_images_encode_the_folded_gemms(name, native):
     assert u == img.size
 
 
+@pytest.mark.parametrize("idim,layers", [(80, 2), (40, 1)])
+def test_gru_tensor_core_weight_stream_encodes_the_gate_matrices(idim, layers, native):
+    """The per-step weight stream of the tensor-core GRU kernel (gru_tc.cu: 16 KB K-major SWIZZLE_128B bf16 chunks of
+    128 hidden units x 64 K, hi chunk then lo chunk per K slab, in the order the MMA issuer consumes them: Linear, then
+    per layer W_hh (r, z, n) and W_ih (r, z, n)) decodes back to the module's own weight matrices."""
+    import ctypes as C
+    import numpy as np
+    cfg = model_config("gru", input_dim=idim)
+    cfg["backbone"]["num_layers"] = layers
+    model = synth.randomize_(init_model(cfg)).eval()
+    h = model._build_handle(finalize=False)
+    lib = native.lib()
+    n = lib.wekws_model_packed_floats(h, 2)
+    nchunk = 2 * ((idim + 63) // 64) + 24 * layers
+    assert n * 4 == nchunk * 16384
+    raw = torch.empty(n, dtype=torch.float32)
+    native.check(lib.wekws_model_packed_copy(h, 2, C.c_void_p(raw.data_ptr()), n), "packed_copy")
+    img = raw.numpy().view(np.uint16)
+    sd = model.state_dict()
+    nn, kk = np.meshgrid(np.arange(128), np.arange(64), indexing="ij")
+    u16 = (nn * 128 + (((kk >> 3) ^ (nn & 7)) << 4) + (kk & 7) * 2) // 2
+
+    def chunk(i):
+        return (img[i * 8192 + u16].astype(np.uint32) << 16).view(np.float32)
+
+    def check(i, W, row0, k0):                       # chunks i (hi), i + 1 (lo) <- W[row0:row0+128, k0:k0+64]
+        w = np.zeros((128, 64), np.float32)
+        kend = min(k0 + 64, W.shape[1])
+        w[:, :kend - k0] = W[row0:row0 + 128, k0:kend]
+        hi, lo = chunk(i), chunk(i + 1)
+        assert np.array_equal(hi, torch.from_numpy(w.copy()).to(torch.bfloat16).float().numpy())
+        assert np.all(np.abs(hi + lo - w) <= 2.0 ** -16 * np.abs(w) + 1e-30)
+
+    i = 0
+    wp = sd["preprocessing.out.0.weight"].numpy()
+    for s in range((idim + 63) // 64):
+        check(i, wp, 0, 64 * s)
+        i += 2
+    for layer in range(layers):
+        for key in ("weight_hh", "weight_ih"):
+            W = sd[f"backbone.{key}_l{layer}"].numpy()
+            for g in range(3):
+                for s in range(2):
+                    check(i, W, 128 * g, 64 * s)
+                    i += 2
+    assert i == nchunk
+
+
 def test_state_dict_schema_and_init_match_reference_golden():
     d = golden("init_digest")
     for name in ("mdtc", "mdtc_small", "ds_tcn", "tcn", "gru"):
