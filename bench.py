@@ -538,7 +538,23 @@ def cpu_baseline_subprocess(workload, orig_affinity, budget_s):
             os.sched_setaffinity(0, cur)
 
 
+class _OnlyTheLine:
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version line on the boxes
+    where NCCL_DEBUG is set), so everything else of this process is sent to stderr: fd 1 is pointed at fd 2 for the
+    whole run and the line is written to the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.fd, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    out = _OnlyTheLine()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -558,7 +574,7 @@ def main():
         if rank != 0:
             return 0
         r = cpu_reference_run(args.workload, args.steps, args.warmup, budget_s=args.cpu_budget)
-        print(json.dumps(reference_line(args, config, r)))
+        out.emit(reference_line(args, config, r))
         return 0
 
     placement, orig_aff = bind_to_gpu_cpus(local)
@@ -595,7 +611,7 @@ def main():
         line["extra_workloads"] = extras
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, orig_aff, budget_s=15.0)
-    print(json.dumps(line))
+    out.emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
