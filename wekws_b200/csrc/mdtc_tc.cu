@@ -333,43 +333,47 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           for (int k = 0; k < ksteps; ++k) umma_bf16_ts(dcol, alo + 8 * k, dW_hi[slot] + 2 * k, idesc, 1);
           for (int k = 0; k < ksteps; ++k) umma_bf16_ts(dcol, ahi + 8 * k, dW_lo[slot] + 2 * k, idesc, 1);
         };
-        // this warp's rows of the operand are in TMEM: warps 1..3 arrive and move on; warp 0 waits for them and issues
-        // GEMM `job` (-1: first Linear over slot 0 (+1); 0 / 1: the block's pointwise-1 / conv2 GEMM over that slot)
+        // this warp's rows of the operand are in TMEM: the tile's other warps arrive and move on, the issuing warp waits
+        // for them and dispatches GEMM `job` (-1: first Linear over slot 0 (+1); 0 / 1: the block's pointwise-1 / conv2
+        // GEMM over that slot).  The two GEMMs of a block are dispatched by DIFFERENT warps (the last lane quarter of
+        // each channel half -- the warps with the fewest live rows in a partly filled tile): a dispatch costs ~660
+        // cycles, and with one warp doing both it was 1.3 k cycles behind its group at every block's barrier.
         auto hand_over = [&](int job) {
+          const int issuer = job == 1 ? WPG - 1 : WPG / NCG - 1;
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (wq != 0) {
+          if (wq != issuer) {
             if (lane == 0) mbar_arrive(&a_rdy[grp]);
-            return;
-          }
-          mbar_wait(&a_rdy[grp], ar_par);
-          ar_par ^= 1;
-          tc_fence_after();
-          // the whole warp runs the issue path (uniform values -> descriptors in uniform registers, every MMA a single
-          // instruction); only the tcgen05 instructions themselves are elected
-          if (job < 0) {
-            mbar_wait(&w_bar[0], w_par & 1);
-            if (natoms > 1) mbar_wait(&w_bar[1], (w_par >> 1) & 1);
-            if (elect_one_sync()) {
-              uint32_t acc = 0;
-              issue_gemm(0, 0, (min(a.idim, 64) + 15) >> 4, acc);
-              if (natoms > 1) issue_gemm(32, 1, (a.idim - 64 + 15) >> 4, acc);
-              umma_commit(&mma_bar[grp]);
-              umma_commit(&w_free[0]);
-              if (natoms > 1) umma_commit(&w_free[1]);
-            }
           } else {
-            mbar_wait(&w_bar[job], (w_par >> job) & 1);
-            if (elect_one_sync()) {
-              uint32_t acc = 0;
-              issue_gemm(0, job, 4, acc);
-              umma_commit(&mma_bar[grp]);
-              umma_commit(&w_free[job]);      // the slot may be refilled once these MMAs are done
+            mbar_wait(&a_rdy[grp], ar_par);
+            tc_fence_after();
+            // the whole warp runs the issue path (uniform values -> descriptors in uniform registers, every MMA a single
+            // instruction); only the tcgen05 instructions themselves are elected
+            if (job < 0) {
+              mbar_wait(&w_bar[0], w_par & 1);
+              if (natoms > 1) mbar_wait(&w_bar[1], (w_par >> 1) & 1);
+              if (elect_one_sync()) {
+                uint32_t acc = 0;
+                issue_gemm(0, 0, (min(a.idim, 64) + 15) >> 4, acc);
+                if (natoms > 1) issue_gemm(32, 1, (a.idim - 64 + 15) >> 4, acc);
+                umma_commit(&mma_bar[grp]);
+                umma_commit(&w_free[0]);
+                if (natoms > 1) umma_commit(&w_free[1]);
+              }
+            } else {
+              mbar_wait(&w_bar[job], (w_par >> job) & 1);
+              if (elect_one_sync()) {
+                uint32_t acc = 0;
+                issue_gemm(0, job, 4, acc);
+                umma_commit(&mma_bar[grp]);
+                umma_commit(&w_free[job]);      // the slot may be refilled once these MMAs are done
+              }
             }
+            __syncwarp();
           }
+          ar_par ^= 1;                          // every warp keeps both phase counters: the issuer changes from GEMM to GEMM
           w_par ^= job < 0 ? (natoms > 1 ? 3u : 1u) : (1u << job);
-          __syncwarp();
         };
         auto wait_mma = [&]() {
           mbar_wait(&mma_bar[grp], mma_par);
@@ -511,7 +515,8 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           {
             const int off = a.coff[blk];
             // lane -> (column j of the slice, channel-quad sub-index): one LDS.128 = 4 channels of one column, then four
-            // stores, each lane-contiguous along a cache row
+            // stores, each lane-contiguous along a cache row (a 4x4 register-transposed variant with 16-byte stores was
+            // measured: no faster, and it spills at 72 registers)
             const int jpl = pad < 32 ? pad : 32, lgj = 31 - __clz(jpl), qstep = 32 >> lgj;
             const int j = lane & (jpl - 1), qs = lane >> lgj, per = 16 >> (5 - lgj);      // quads passes per stream
             const int nitem = nst * per;
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
           TPH(t_gb)
         }
 #if MDTC_TIMING
-        if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5 || warp == 8 || warp == 16))
+        if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 3 || warp == 7 || warp == 16))
           printf("warp %2d: blocks %lld cycles | halo %lld dw %lld handover0 %lld cache-store %lld wait1 %lld epi1 %lld handover1 %lld wait2 %lld epi2 %lld barrier %lld\n",
                  warp, clock64() - t_blocks0, t_halo, t_dw, t_ho0, t_cs, t_w1, t_e1, t_ho1, t_w2, t_e2, t_gb);
 #endif
