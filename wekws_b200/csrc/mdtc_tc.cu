@@ -60,12 +60,11 @@ constexpr int X_BYTES = XCOLS * 256;       // 129024: X[col][64] fp32
 constexpr int STG_FLOATS = 64 * 32;        // TMA landing slot: one stream's cache slice [64][pad <= 32]
 constexpr int NSLOT = 7;                   // TMA landing slots, shared out among the tiles' loaders by stream count
 constexpr int W_SLOT = 16384;              // hi + lo image of one 64x64 matrix
-constexpr int VEC_FLOATS = 64;             // per-block vector kept in shared memory: the folded depthwise bias (all blocks preloaded)
 constexpr int OFF_X = 0;
 constexpr int OFF_STG = OFF_X + X_BYTES;                   // 129024
 constexpr int OFF_W = OFF_STG + NSLOT * STG_FLOATS * 4;    // 186368 (1024-aligned: SWIZZLE_128B images)
-constexpr int OFF_VEC = OFF_W + 2 * W_SLOT;                // 219136
-constexpr int SMEM_TOTAL = OFF_VEC + kTcMaxBlocks * VEC_FLOATS * 4 + 1024;   // 224512 incl. alignment slack
+constexpr int OFF_END = OFF_W + 2 * W_SLOT;                // 219136
+constexpr int SMEM_TOTAL = OFF_END + 1024;                 // incl. alignment slack
 static_assert(OFF_W % 1024 == 0, "weight images must be 1024-byte aligned");
 static_assert(SMEM_TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 // TMEM columns of tile i: [160 i, 160 i + 64) accumulator, + 64.. A hi (<= 48 cols = K 96), + 112.. A lo
@@ -94,16 +93,10 @@ struct Bars {
 __device__ __noinline__ void weights_role(const TcArgs& a, uint8_t* base, Bars B, int K, int natoms, uint32_t& wf_par,
                                           bool first_pass) {
   uint8_t* Wslot[2] = {base + OFF_W, base + OFF_W + W_SLOT};
-  float* VEC = reinterpret_cast<float*>(base + OFF_VEC);
   auto load_w = [&](int slot, const uint8_t* src) {
     mbar_arrive_expect_tx(&B.w_bar[slot], W_SLOT);
     bulk_g2s(Wslot[slot], src, W_SLOT, &B.w_bar[slot]);
   };
-  if (first_pass) {                            // folded depthwise biases of ALL blocks, once per launch -> VEC[blk]
-    mbar_arrive_expect_tx(&B.vec_bar[0], (uint32_t)(a.nblocks * C * 4));
-    for (int blk = 0; blk < a.nblocks; ++blk)
-      bulk_g2s(VEC + blk * VEC_FLOATS, a.vec + a.v_blocks + blk * a.v_blk_stride + K * C, (uint32_t)(C * 4), &B.vec_bar[0]);
-  }
   auto wait_free = [&](int slot) {             // every tile's MMAs on the slot's current weights are done
     mbar_wait_backoff(&B.w_free[slot], (wf_par >> slot) & 1);
     wf_par ^= 1u << slot;
@@ -273,7 +266,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
   const uint32_t tmem = uniform32(tmem_slot);        // warp-uniform: MMA operands are then built in uniform registers
   const Bars bars{mma_bar, halo_bar, a_rdy, h_free, w_bar, w_free, vec_bar, stg_bar};
   // phase parities: every waiter keeps its own copy; all copies of a barrier advance in lock step
-  uint32_t mma_par = 0, halo_par = 0, ar_par = 0, vec_par = 0, tok_par = 0;   // compute groups
+  uint32_t mma_par = 0, halo_par = 0, ar_par = 0, tok_par = 0;       // compute groups
   uint32_t hf_par = 0;                                               // loaders: bit i = tile i
   uint32_t w_par = 0, wf_par = 0;                                    // bit s = slot s
   const uint32_t idesc = make_idesc_bf16(128, 64);
@@ -313,7 +306,6 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
         const int col = sg * Lw + PADR + tt;               // this row's frame column (dead rows alias a valid one)
         const uint32_t t_own = xs + ((uint32_t)col << 8) + (((uint32_t)col & 7u) << 4);
         const uint32_t tm_row = tmem + ((uint32_t)(32 * q) << 16) + TM_TILE * grp;
-        const uint32_t vsm = sbase + OFF_VEC;
         float part[8];                                     // classifier partial sums of this row
 #pragma unroll
         for (int j = 0; j < 8; ++j) part[j] = 0.f;
@@ -440,13 +432,8 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
 #endif
         for (int blk = 0; blk < a.nblocks; ++blk) {
           const int d = a.dil[blk], pad = d * (K - 1);
-          const uint32_t vb = vsm + (uint32_t)blk * (VEC_FLOATS * 4);
           const bool stack_end = (blk > 0) && (blk % a.stack_size == 0);
           // ---------------- depthwise dilated conv (+folded BN) -> operand rows in TMEM      (mdtc.py:56-57)
-          if (vec_par == 0) {                 // the biases of all blocks land once per launch
-            mbar_wait(&vec_bar[0], 0);
-            vec_par = 1;
-          }
           mbar_wait(&halo_bar[grp], halo_par);
           halo_par ^= 1;
           TPH(t_halo)
@@ -469,9 +456,9 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
 #pragma unroll
             for (int mi = 0; mi < 8 / NCG; ++mi) {
               const int m = (8 / NCG) * g + mi;
-              f32x2 acc0, acc1, acc2, acc3;
-              lds_2x2(vb + (uint32_t)(8 * m) * 4, acc0, acc1);          // folded depthwise bias (VEC holds only this now)
-              lds_2x2(vb + (uint32_t)(8 * m) * 4 + 16, acc2, acc3);
+              // (the folded depthwise bias is not added here: the host folds it through the pointwise-1 matrix into b1,
+              // model_host.cu pack_tc -- it was 8 of the 48 LDS.128 per thread of this shared-memory-bound loop)
+              f32x2 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
 #pragma unroll
               for (int j = 0; j < 5; ++j) {
                 if (KT ? j < KT : j < K) {

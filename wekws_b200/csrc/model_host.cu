@@ -325,8 +325,14 @@ void pack_tc(wekws_model* m) {
     float* dst = reinterpret_cast<float*>(&t.cw[b][0]);
     for (int j = 0; j < 5; ++j)
       for (int ch = 0; ch < 64; ++ch) dst[j * 64 + ch] = j < a.ktaps ? vb[j * 64 + ch] : 0.f;
+    // the folded depthwise bias goes through the pointwise-1 matrix into b1 (h = relu(W1 (dw + b_dw) + b1)), so the
+    // depthwise loop of the kernel starts from zero instead of loading a per-channel bias
+    const float* w1t = m->folded[1 + 2 * b].data();     // W1^T [k][n]
+    const float* bdw = vb + a.ktaps * 64;
     for (int ch = 0; ch < 64; ++ch) {
-      dst[5 * 64 + ch] = vb[(a.ktaps + 1) * 64 + ch];
+      double acc = vb[(a.ktaps + 1) * 64 + ch];
+      for (int k = 0; k < 64; ++k) acc += (double)w1t[(size_t)k * 64 + ch] * (double)bdw[k];
+      dst[5 * 64 + ch] = (float)acc;
       dst[6 * 64 + ch] = vb[(a.ktaps + 2) * 64 + ch];
     }
   }
