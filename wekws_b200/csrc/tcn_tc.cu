@@ -17,6 +17,16 @@
 #include "tc_common.cuh"
 #include "tcn_tc.h"
 
+// per-phase cycle counters (debug builds with -DTCN_TIMING=1 only)
+#ifndef TCN_TIMING
+#define TCN_TIMING 0
+#endif
+#if TCN_TIMING
+#define TPH(acc) { const long long t_now_ = clock64(); acc += t_now_ - t_last_; t_last_ = t_now_; }
+#else
+#define TPH(acc)
+#endif
+
 namespace wekws {
 
 namespace {
@@ -190,40 +200,13 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
         witem += (uint32_t)nitems;
       }
     } else if (is_loader) {
-      // ================================================================== LOADER WARPS (4-byte cp.async into X)
-      const int l = warp - NCW - 1;
-      for (int blk = 0; blk < a.nblocks; ++blk) {
-        const int pad = a.dil[blk] * (K - 1), off = a.coff[blk];
-        for (int i = 0; i < ntile; ++i) {
-          wd_mark(1000000 + blk * 10 + i);
-          if (blk > 0) {
-            if (lane == 0) mbar_wait_backoff(&h_free[i], (hf_par >> i) & 1);
-            hf_par ^= 1u << i;
-            __syncwarp();
-          }
-          for (int sg = i * spt; sg < i * spt + tile_streams(i); ++sg) {
-            if ((sg & 1) != l) continue;
-            const float* src0 = a.in_cache ? a.in_cache + (size_t)(b0 + sg) * C * a.P + off : nullptr;
-            float* dst0 = X + sg * Lw + PADR - pad;
-            for (int e = lane; e < C * pad; e += 32) {
-              const int c = e / pad, p = e - c * pad;
-              if (src0) cp_async4(dst0 + c * RPX + p, src0 + (size_t)c * a.P + p);
-              else dst0[c * RPX + p] = 0.f;
-            }
-          }
-          asm volatile("cp.async.wait_all;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&halo_bar[i]);
-          wd_mark(2000000 + blk * 10 + i);
-        }
-      }
-      for (int i = 0; i < ntile; ++i) {
-        if (lane == 0) mbar_wait_backoff(&h_free[i], (hf_par >> i) & 1);
-        hf_par ^= 1u << i;
-      }
+      // (no loader role any more: the compute warps fetch the next block's cache slices themselves, see load_halo)
     } else {
       // ================================================================== COMPUTE WARPS
       int colx[NTILE], rows_i[NTILE];
+#if TCN_TIMING
+      long long t_halo = 0, t_abf = 0, t_stage = 0, t_ho = 0, t_cs = 0, t_wm = 0, t_epi = 0, t_bar = 0, t_last_ = 0;
+#endif
 #pragma unroll
       for (int i = 0; i < NTILE; ++i) {
         rows_i[i] = i < ntile ? tile_streams(i) * T : 0;
@@ -295,15 +278,13 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
         constexpr int i = decltype(tc)::value;
         const int b = j & 1;
         wd_mark(1000000 + blk * 1000 + j * 10 + i);
-        if (j == 0) {                                // this tile's cache slice is in place
-          mbar_wait(&halo_bar[i], (halo_par >> i) & 1);
-          halo_par ^= 1u << i;
-        }
+        // (the tile's cache slice is in place: load_halo + the barrier at the end of the previous block)
         if (j >= 2) {                                // the MMAs of tap j-2 have drained this buffer
           const uint32_t cidx = ab_cnt[i][b] + (uint32_t)(j >> 1) - 1u;
           mbar_wait(&ab_free[i][b], cidx & 1);
           tc_fence_after();
         }
+        TPH(t_abf)
         wd_mark(3000000 + blk * 1000 + j * 10 + i);
         if (q_live[i]) {
 #pragma unroll
@@ -316,10 +297,29 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
             split_to_tmem(v, tm_row + TM_TILE * i + 64 + 64 * b + 4 * cg, tm_row + TM_TILE * i + 96 + 64 * b + 4 * cg);
           }
         }
+        TPH(t_stage)
         hand_over(tc, b);
+        TPH(t_ho)
         wd_mark(4000000 + blk * 1000 + j * 10 + i);
       };
-      // new cache slices (tcn.py:54), then release the cache columns to the loaders
+      // Cache slices of block `blk` -> the pad columns in front of every stream's frames, 4-byte cp.async (rows of the
+      // cache are 105 floats, slices 7..56: nothing is 16-byte aligned), spread over ALL compute threads and issued one
+      // block ahead, right after the last tap that reads the current block's slices -- the copies then overlap the last
+      // tap, its GEMM and the epilogue; `halo_wait` + the block barrier publish them.  (Two dedicated loader warps with
+      // a per-element division needed ~17 k cycles per block and the compute warps spent 55 % of their time waiting
+      // for them: clock64 counters, profiles/r02_tcn_notes.md.)
+      auto load_halo = [&](int blk) {
+        const int pad = a.dil[blk] * (K - 1), off = a.coff[blk];
+        const int per = C * pad;
+        for (int e = tid; e < ns * per; e += NCT) {
+          const int sg = e / per, r = e - sg * per, c = r / pad, p = r - c * pad;
+          float* dst = X + c * RPX + sg * Lw + PADR - pad + p;
+          if (a.in_cache) cp_async4(dst, a.in_cache + ((size_t)(b0 + sg) * C + c) * a.P + off + p);
+          else *dst = 0.f;
+        }
+      };
+      auto halo_wait = [&]() { asm volatile("cp.async.wait_all;\n" ::: "memory"); };
+      // new cache slices (tcn.py:54); afterwards nobody reads the block's cache columns again
       auto store_cache = [&](int blk, int pad) {
         const int off = a.coff[blk];
         for (int i = 0; i < ntile; ++i) {
@@ -330,8 +330,12 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
           }
         }
         __syncwarp();
-        if (lane == 0)
-          for (int i = 0; i < ntile; ++i) mbar_arrive(&h_free[i]);
+        if (lane == 0) mbar_arrive(&h_free[0]);
+      };
+      // every compute warp is past the taps (and cache stores) that read the current slices: the columns may be rewritten
+      auto halo_free_wait = [&]() {
+        mbar_wait(&h_free[0], hf_par & 1);
+        hf_par ^= 1u;
       };
       // x' = relu(D + b) + x -> X                                          (tcn.py:60: no ReLU after the add)
       auto epi = [&](auto tc, int blk) {
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
         const float* bb = vec + a.v_blocks + blk * a.v_blk_stride + 16 * g;
         wd_mark(5000000 + blk * 1000 + i);
         wait_mma(tc);
+        TPH(t_wm)
         wd_mark(6000000 + blk * 1000 + i);
         if (!q_live[i]) return;
         float d[16];
@@ -359,23 +364,35 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
       constexpr std::integral_constant<int, 0> T0{};
       constexpr std::integral_constant<int, 1> T1{};
       wd_mark(1);
+      load_halo(0);                                  // overlaps the feature load and the first Linear
       feat(T0);
       if (ntile > 1) feat(T1);
       wd_mark(2);
       epi0(T0);
       if (ntile > 1) epi0(T1);
       wd_mark(3);
+      halo_wait();
       tc_fence_before();
       compute_barrier();
       wd_mark(4);
 
+#if TCN_TIMING
+      t_last_ = clock64();
+      const long long t_begin_ = t_last_;
+#endif
       for (int blk = 0; blk < a.nblocks; ++blk) {
         const int d = a.dil[blk], pad = d * (K - 1);
         for (int j = 0; j < K; ++j) {
           // The last tap reads frames only (position t + pad), never the cache columns: store the new cache slices
           // and release the columns before it.  The stores then precede this warp's last hand-over, hence the last
           // GEMM and the epilogue (which overwrites x) cannot start before every warp's stores have been issued.
-          if (j == K - 1) store_cache(blk, pad);
+          if (j == K - 1) {
+            store_cache(blk, pad);
+            TPH(t_cs)
+            halo_free_wait();
+            if (blk + 1 < a.nblocks) load_halo(blk + 1);
+            TPH(t_halo)
+          }
           tap(T0, blk, j, d, pad);
           if (ntile > 1) tap(T1, blk, j, d, pad);
         }
@@ -384,9 +401,17 @@ __global__ void __launch_bounds__(NT_TC, 1) tcn_tc_kernel(const TcnTcArgs a) {
           if (i < ntile) { ab_cnt[i][0] += (uint32_t)((K + 1) >> 1); ab_cnt[i][1] += (uint32_t)(K >> 1); }
         epi(T0, blk);
         if (ntile > 1) epi(T1, blk);
+        TPH(t_epi)
+        halo_wait();
         tc_fence_before();
         compute_barrier();
+        TPH(t_bar)
       }
+#if TCN_TIMING
+      if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7))
+        printf("tcn warp %d pass(ns=%d): blocks %lld cycles | halo %lld ab_free %lld staging %lld handover %lld cache-store %lld wait-mma %lld epilogue %lld barrier %lld\n",
+               warp, ns, clock64() - t_begin_, t_halo, t_abf, t_stage, t_ho, t_cs, t_wm, t_epi, t_bar);
+#endif
 
       // ---- classifier + activation on x (tcn.py:165 -> classifier.py:63-67)
       const int odim = a.odim;
