@@ -494,6 +494,8 @@ class Runner:
                     "h2d_bytes_per_step": (B * PCM_SAMPLES * 2) if pcm_mode else (B * T * idim * 4),
                     "d2h_bytes_per_step": B * T * model.odim * 4, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "batch_latency": e2e_lat,
+                    # what bounds the end-to-end number: the step's input crosses PCIe once (Gen5 x16: ~55 GB/s in practice)
+                    "h2d_gb_per_s": ((B * PCM_SAMPLES * 2) if pcm_mode else (B * T * idim * 4)) / (e2e_ms / e2e_steps * 1e-3) / 1e9,
                     "api": ("wekws_b200.Pipeline(Fbank, KWSModel)(pcm) -> wekws_pipeline_forward" if pcm_mode else "wekws_b200.KWSModel.forward(feats, cache)")
                            + "; pinned host input in, posteriors out, H2D double-buffered on a copy stream; "
                              "own step count: warm-up until stable (>= 0.5 s), then >= 1 s timed"},

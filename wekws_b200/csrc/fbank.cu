@@ -9,14 +9,18 @@
 //
 // One warp owns one frame for the FFT.  The 512-point real FFT is a 256-point complex FFT of the
 // even/odd packed frame, done as a radix-8 / radix-8 / radix-4 Stockham autosort with the
-// first radix-8 entirely in registers (lane p holds z[p + 32 r]) and two exchanges through
-// bank-conflict-free padded per-warp shared buffers; lane-constant twiddles live in
-// registers.  A CTA (8 warps) stages the 5360 samples its 32 consecutive frames need once
-// (16-byte loads), so each PCM byte is read from HBM ~1.05x and each output byte written once.
+// first radix-8 entirely in registers (lane p holds z[p + 32 r]), two exchanges through one
+// bank-conflict-free padded per-warp shared buffer, and the real-FFT untangle by warp shuffles;
+// lane-constant twiddles live in registers.  A CTA (8 warps) stages the 5360 samples its 32
+// consecutive frames need once (16-byte loads, kept in the PCM type: int16 audio costs 10.5 KB),
+// so each PCM byte is read from HBM ~1.05x and each output byte written once.  The log-mel kernel
+// is sized for THREE CTAs per SM (73 KB of shared memory, <= 80 registers): 24 warps hide the
+// shared-memory and shuffle latencies of the FFT better than the 16 of the round-2 kernel.
 // The mel projection runs after all 32 power spectra of the work item are in shared memory, with
 // lane = frame and the (warp-uniform) sparse row of one mel bin per warp: no divergence between
 // lanes whatever the filter widths, 3 instructions per tap per 32 frames.
 #include <math.h>
+#include <string.h>
 #include <vector>
 
 #include "common.cuh"
@@ -30,7 +34,7 @@ constexpr int FB_WARPS = 8;                 // warps per CTA
 constexpr int FB_FPW = 4;                   // frames per warp per work item
 constexpr int FB_FRAMES = FB_WARPS * FB_FPW; // frames per CTA work item (one staging load)
 constexpr int FB_NT = FB_WARPS * 32;
-using fbcore::WIN; using fbcore::SHIFT; using fbcore::NFFT; using fbcore::NBIN; using fbcore::A_SZ; using fbcore::B_SZ;
+using fbcore::WIN; using fbcore::SHIFT; using fbcore::NFFT; using fbcore::NBIN; using fbcore::B_SZ;
 constexpr int STAGE = (FB_FRAMES - 1) * SHIFT + WIN;  // 5360 samples
 constexpr int MAX_MEL = 128;
 constexpr int P_ST = NBIN + 1;              // row pitch of the power-spectrum tile (odd: lane = frame reads are conflict-free)
@@ -38,7 +42,11 @@ constexpr int O_ST = MAX_MEL + 1;           // row pitch of the output staging t
 static_assert(FB_FRAMES == 32, "the mel phase maps one frame to one lane");
 static_assert(FB_FRAMES * O_ST <= STAGE, "output staging must fit in the PCM stage");
 static_assert(STAGE % 8 == 0, "vector staging");
-constexpr int SMEM_FLOATS_COMMON = STAGE + FB_WARPS * 2 * (A_SZ + B_SZ) + 2 * NBIN + WIN + 2 * NBIN + 64 + 3 * MAX_MEL;
+// shared-memory layout (floats): [PCM stage as float / output tile][exchange buffers][tw512][window]
+// [log-mel kernel: power tile | MFCC kernel: mel weights]
+constexpr int MW_MAX = 2 * NBIN + 64;       // non-zero mel weights supported (80 bins at 16 kHz: 501)
+constexpr int SMEM_FLOATS_COMMON = STAGE + FB_WARPS * 2 * B_SZ + 2 * NBIN + WIN;
+static_assert((SMEM_FLOATS_COMMON + FB_FRAMES * P_ST) * 4 + 1024 <= 233472 / 3, "the log-mel kernel must fit three times per SM");
 
 struct FbankArgs {
   const void* pcm;
@@ -66,33 +74,40 @@ struct FbankArgs {
   int nceps, odim;          // odim = row width of `out` (nceps in MFCC mode, else nmel)
 };
 
+// The sparse mel filterbank of the log-mel kernel travels in the kernel-parameter constant bank: in the mel phase a
+// warp works on ONE mel bin at a time (lane = frame), so the row's start / length / weights are warp-uniform and come
+// through the uniform datapath (LDCU) instead of competing with the per-lane spectrum loads for the shared-memory
+// pipe -- and the 3.8 KB of tables they used to occupy there is what lets a third CTA fit on the SM.
+struct MelTable {
+  float w[MW_MAX];                          // non-zero weights, row after row
+  int16_t start[MAX_MEL], cnt[MAX_MEL], off[MAX_MEL];   // per mel bin: first fft bin, taps, offset into w
+};
+
 // MFCC = true adds the cepstral epilogue: the log-mel rows of the warp's FB_FPW frames stay in registers
 // (lane owns bins lane + 32 k) and are multiplied with the DCT matrix together, so every matrix element is
 // loaded once per FB_FPW frames and 12-16 accumulators run in parallel.
 template <typename PCM, bool MFCC>
-__global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
+__global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankArgs a, const __grid_constant__ MelTable mt) {
   extern __shared__ __align__(16) float fb_smem[];
   float* s_stage = fb_smem;                                              // [STAGE]
-  float (*s_bufA)[2][A_SZ] = reinterpret_cast<float (*)[2][A_SZ]>(s_stage + STAGE);
-  float (*s_bufB)[2][B_SZ] = reinterpret_cast<float (*)[2][B_SZ]>(s_stage + STAGE + FB_WARPS * 2 * A_SZ);
-  float2* s_tw512 = reinterpret_cast<float2*>(s_stage + STAGE + FB_WARPS * 2 * (A_SZ + B_SZ));
+  float (*s_bufB)[2][B_SZ] = reinterpret_cast<float (*)[2][B_SZ]>(s_stage + STAGE);
+  float2* s_tw512 = reinterpret_cast<float2*>(s_stage + STAGE + FB_WARPS * 2 * B_SZ);
   float2* s_win = s_tw512 + NBIN;
-  float* s_mw = reinterpret_cast<float*>(s_win + WIN / 2);               // [2 * NBIN + 64]
-  int* s_mtab = reinterpret_cast<int*>(s_mw + 2 * NBIN + 64);            // [3][MAX_MEL]: first bin, count, offset into s_mw
-  float* s_pow = reinterpret_cast<float*>(s_mtab + 3 * MAX_MEL);         // [FB_FRAMES][P_ST] (log-mel kernel only)
+  float* s_pow = reinterpret_cast<float*>(s_win + WIN / 2);              // [FB_FRAMES][P_ST] (log-mel kernel)
+  float* s_mw = s_pow;                                                   // [MW_MAX] (MFCC kernel: per-lane mel rows)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp-uniform for the compiler too: the per-frame branches below are then uniform and the shuffles inside them
+  // need no WARPSYNC / collective bracket
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   for (int i = tid; i < NBIN; i += FB_NT) s_tw512[i] = a.tw512[i];
   for (int i = tid; i < WIN / 2; i += FB_NT) s_win[i] = make_float2(a.window[2 * i], a.window[2 * i + 1]);
-  for (int i = tid; i < a.mw_total; i += FB_NT) s_mw[i] = a.mw[i];
-  for (int i = tid; i < a.nmel; i += FB_NT) {
-    s_mtab[i] = a.mstart[i]; s_mtab[MAX_MEL + i] = a.mcnt[i]; s_mtab[2 * MAX_MEL + i] = a.moff[i];
-  }
+  if (MFCC)
+    for (int i = tid; i < a.mw_total; i += FB_NT) s_mw[i] = a.mw[i];
 
   fbcore::LaneTwiddles tw;
   tw.load(a.tw256, lane);
 
-  float* Ar = s_bufA[warp][0]; float* Ai = s_bufA[warp][1];
   float* Br = s_bufB[warp][0]; float* Bi = s_bufB[warp][1];
 
   const long long nfb = (a.max_frames + FB_FRAMES - 1) / FB_FRAMES;
@@ -149,9 +164,8 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
       for (int fi = 0; fi < FB_FPW; ++fi) {
         const int fl = warp + FB_WARPS * fi;
         if (f0 + fl < mb) {
-          const float* s = s_stage + fl * SHIFT;
-          fbcore::frame_power_spectrum([&](int n) { return s[n]; }, s_win, s_tw512, tw, Ar, Ai, Br, Bi, s_pow + fl * P_ST,
-                                       a.preemph, a.remove_dc, lane);
+          fbcore::frame_power_spectrum(s_stage + fl * SHIFT, s_win, s_tw512, tw, Br, Bi, s_pow + fl * P_ST, a.preemph,
+                                       a.remove_dc, lane);
         }
       }
       __syncthreads();                              // spectra complete; the PCM stage is dead and becomes the output tile
@@ -161,12 +175,11 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
       {
         const float* prow = s_pow + lane * P_ST;
         for (int m = warp; m < a.nmel; m += FB_WARPS) {
-          const int st = s_mtab[m], cnt = s_mtab[MAX_MEL + m];
-          const float* w = s_mw + s_mtab[2 * MAX_MEL + m];
+          const int st = mt.start[m], cnt = mt.cnt[m], off = mt.off[m];      // warp-uniform: constant bank
           const float* p = prow + st;
           float e = 0.f;
 #pragma unroll 4
-          for (int i = 0; i < cnt; ++i) e = fmaf(w[i], p[i], e);
+          for (int i = 0; i < cnt; ++i) e = fmaf(mt.w[off + i], p[i], e);
           float v = logf(fmaxf(e, a.log_floor));
           if (a.mean) v -= __ldg(a.mean + m);
           if (a.istd) v *= __ldg(a.istd + m);
@@ -203,8 +216,7 @@ __global__ void __launch_bounds__(FB_NT) fbank_kernel(const FbankArgs a) {
       continue;
     }
 
-    const float* s = s_stage + fl * SHIFT;
-    fbcore::frame_power_spectrum([&](int n) { return s[n]; }, s_win, s_tw512, tw, Ar, Ai, Br, Bi, Br, a.preemph, a.remove_dc, lane);
+    fbcore::frame_power_spectrum(s_stage + fl * SHIFT, s_win, s_tw512, tw, Br, Bi, Br, a.preemph, a.remove_dc, lane);
     __syncwarp();
     // ---- mel projection (sparse rows), log floor ----
     {
@@ -290,6 +302,7 @@ struct wekws_fbank {
   int* d_moff = nullptr;
   float* d_mw = nullptr;
   int mw_total = 0;
+  MelTable mt;              // host copy of the filterbank rows: passed by value to the log-mel kernel
   int nceps = 0;            // > 0: MFCC mode (wekws_fbank_set_mfcc)
   float* d_dct = nullptr;
   float* d_lifter = nullptr;
@@ -321,13 +334,18 @@ extern "C" int wekws_fbank_create(const wekws_fbank_config* cfg, const float* h_
     moff[m] = (int)mw.size();
     for (int k = 0; k < mcnt[m]; ++k) mw.push_back(h_mel[m * NBIN + mstart[m] + k]);
   }
-  WEKWS_REQUIRE(mw.size() <= 2 * NBIN + 64, "fbank: mel filterbank has %zu non-zeros, more than the %d supported",
-                mw.size(), 2 * NBIN + 64);
+  WEKWS_REQUIRE(mw.size() <= (size_t)MW_MAX, "fbank: mel filterbank has %zu non-zeros, more than the %d supported",
+                mw.size(), MW_MAX);
   if (mw.empty()) mw.push_back(0.f);
   wekws_fbank* fb = new (std::nothrow) wekws_fbank();
   if (!fb) { set_error("out of host memory"); return WEKWS_ERR_NOMEM; }
   fb->cfg = *cfg;
   fb->mw_total = (int)mw.size();
+  memset(&fb->mt, 0, sizeof(fb->mt));
+  for (size_t i = 0; i < mw.size(); ++i) fb->mt.w[i] = mw[i];
+  for (int m = 0; m < nm; ++m) {
+    fb->mt.start[m] = (int16_t)mstart[m]; fb->mt.cnt[m] = (int16_t)mcnt[m]; fb->mt.off[m] = (int16_t)moff[m];
+  }
   WEKWS_CUDA_OK(cudaGetDevice(&fb->device));
 #define UP(dst, vec)                                                                      \
   WEKWS_CUDA_OK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                   \
@@ -403,8 +421,8 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.odim = fb->nceps > 0 ? fb->nceps : fb->cfg.num_mel_bins;
   const long long items = B * ((max_frames + FB_FRAMES - 1) / FB_FRAMES);
   const bool mf = fb->nceps > 0;
-  const size_t smem = (size_t)(SMEM_FLOATS_COMMON + (mf ? 0 : FB_FRAMES * P_ST)) * sizeof(float);
   const int esz = pcm_dtype == WEKWS_PCM_S16 ? 2 : 4;
+  const size_t smem = (size_t)(SMEM_FLOATS_COMMON + (mf ? MW_MAX : FB_FRAMES * P_ST)) * sizeof(float);
   a.vec_ok = (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0 && ((pcm_stride * esz) & 15) == 0;
   int dev = 0;
   WEKWS_CUDA_OK(cudaGetDevice(&dev));
@@ -424,10 +442,10 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   const int grid = (int)(items < cap ? items : cap);
   cudaStream_t st = (cudaStream_t)stream;
   switch (ti) {
-    case 0: fbank_kernel<int16_t, false><<<grid, FB_NT, smem, st>>>(a); break;
-    case 1: fbank_kernel<float, false><<<grid, FB_NT, smem, st>>>(a); break;
-    case 2: fbank_kernel<int16_t, true><<<grid, FB_NT, smem, st>>>(a); break;
-    default: fbank_kernel<float, true><<<grid, FB_NT, smem, st>>>(a); break;
+    case 0: fbank_kernel<int16_t, false><<<grid, FB_NT, smem, st>>>(a, fb->mt); break;
+    case 1: fbank_kernel<float, false><<<grid, FB_NT, smem, st>>>(a, fb->mt); break;
+    case 2: fbank_kernel<int16_t, true><<<grid, FB_NT, smem, st>>>(a, fb->mt); break;
+    default: fbank_kernel<float, true><<<grid, FB_NT, smem, st>>>(a, fb->mt); break;
   }
   return check_launch("fbank_kernel");
 }

@@ -1,15 +1,16 @@
-// Per-frame core of the Kaldi-compatible Fbank front-end, shared by fbank.cu (stand-alone kernel) and mdtc_tc.cu (raw
-// PCM -> posterior in one launch): DC removal, pre-emphasis with replicate padding, window, 512-point real FFT as a
-// 256-point complex FFT (radix 8 / 8 / 4 Stockham, first radix-8 in registers, two exchanges through padded per-warp
-// shared buffers), untangle + power spectrum.  One warp per frame.  torchaudio kaldi.py:183-211, 616-618.
+// Per-frame core of the Kaldi-compatible Fbank front-end (fbank.cu): DC removal, pre-emphasis with replicate padding,
+// window, 512-point real FFT as a 256-point complex FFT (radix 8 / 8 / 4 Stockham, first radix-8 in registers, two
+// exchanges through ONE padded per-warp shared buffer, last pass left in registers), untangle by warp shuffles + power
+// spectrum.  One warp per frame.  torchaudio kaldi.py:183-211, 616-618.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace wekws {
 namespace fbcore {
 
 constexpr int WIN = 400, SHIFT = 160, NFFT = 512, NBIN = 256;
-constexpr int A_SZ = 264, B_SZ = 280;       // padded exchange buffers (floats)
+constexpr int B_SZ = 280;                   // padded exchange buffer (floats): holds the piA (264) and the piB (280) layout
 
 __device__ __forceinline__ int piA(int i) { return i + (i >> 5); }
 __device__ __forceinline__ int piB(int i) { return i + 8 * (i >> 6); }
@@ -55,103 +56,115 @@ struct LaneTwiddles {
   }
 };
 
-// Power spectrum of one frame -> pw[0..255].  `s(n)`: sample n (0..399) of the frame as float (int16 scale).
-// Ar/Ai: A_SZ floats each, Br/Bi: B_SZ floats each, private to the warp; pw may be Br.  s_win: window as (even, odd) pairs; s_tw512:
-// W_512^k, k < 256.  All 32 lanes participate.
-template <typename Sample>
-__device__ __forceinline__ void frame_power_spectrum(Sample s_, const float2* __restrict__ s_win,
-                                                     const float2* __restrict__ s_tw512, const LaneTwiddles& tw, float* Ar,
-                                                     float* Ai, float* Br, float* Bi, float* pw, float preemph, int remove_dc, int lane) {
+// Power spectrum of one frame -> pw[0..255].  s: the frame's 400 samples as float (int16 scale).  Er/Ei: B_SZ floats each, private to the warp (both exchanges go through
+// them; pw may be Er).  s_win: window as (even, odd) pairs; s_tw512: W_512^k, k < 256.  All 32 lanes participate.
+// After the last radix-4 pass lane l holds Z[l + 32 i], i < 8, in registers; the real-FFT untangle needs Z[256 - k]
+// next to Z[k], which is element 7 - i of lane 32 - l (lane 0: its own element (8 - i) & 7) -- 16 shuffles instead
+// of a third trip through shared memory.
+__device__ __forceinline__ void frame_power_spectrum(const float* __restrict__ s, const float2* __restrict__ s_win,
+                                                     const float2* __restrict__ s_tw512, const LaneTwiddles& tw, float* Er,
+                                                     float* Ei, float* pw, float preemph, int remove_dc, int lane) {
   const float* t1r = tw.t1r; const float* t1i = tw.t1i; const float* t2r = tw.t2r; const float* t2i = tw.t2i;
-    // ---- window: lane owns packed points m = lane + 32 i (even/odd sample pair 2m, 2m+1) ----
-    float xa[7], xb[7], xc[7];
-    float sum = 0.f;
+  // ---- window: lane owns packed points m = lane + 32 i (even/odd sample pair 2m, 2m+1) ----
+  float xa[7], xb[7], xc[7];
+  float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const int m = lane + 32 * i;
-      if (m < WIN / 2) {
-        xb[i] = s_(2 * m); xc[i] = s_(2 * m + 1);
-        xa[i] = m > 0 ? s_(2 * m - 1) : xb[i];          // replicate pad (kaldi.py:195)
-        sum += xb[i] + xc[i];
-      } else {
-        xa[i] = xb[i] = xc[i] = 0.f;
-      }
+  for (int i = 0; i < 7; ++i) {
+    const int m = lane + 32 * i;
+    if (m < WIN / 2) {
+      const float2 v = *reinterpret_cast<const float2*>(s + 2 * m);
+      xb[i] = v.x; xc[i] = v.y;
+      xa[i] = m > 0 ? s[2 * m - 1] : xb[i];           // replicate pad (kaldi.py:195)
+      sum += xb[i] + xc[i];
+    } else {
+      xa[i] = xb[i] = xc[i] = 0.f;
     }
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = remove_dc ? sum / (float)WIN : 0.f;
-    float zr[8], zi[8];
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = remove_dc ? sum / (float)WIN : 0.f;
+  float zr[8], zi[8];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const int m = lane + 32 * i;
-      if (m < WIN / 2) {
-        const float2 w = s_win[m];
-        const float pa = xa[i] - mean, pb = xb[i] - mean, pc = xc[i] - mean;
-        zr[i] = (pb - preemph * pa) * w.x;
-        zi[i] = (pc - preemph * pb) * w.y;
-      } else {
-        zr[i] = 0.f; zi[i] = 0.f;
-      }
+  for (int i = 0; i < 7; ++i) {
+    const int m = lane + 32 * i;
+    if (m < WIN / 2) {
+      const float2 w = s_win[m];
+      const float pa = xa[i] - mean, pb = xb[i] - mean, pc = xc[i] - mean;
+      zr[i] = (pb - preemph * pa) * w.x;
+      zi[i] = (pc - preemph * pb) * w.y;
+    } else {
+      zr[i] = 0.f; zi[i] = 0.f;
     }
-    zr[7] = 0.f; zi[7] = 0.f;
+  }
+  zr[7] = 0.f; zi[7] = 0.f;
 
-    // ---- pass 1: radix 8 over r (n=256, s=1) -> A[8p + k] * W_256^(pk) ----
-    dft8(zr, zi);
+  // ---- pass 1: radix 8 over r (n=256, s=1) -> E[8p + k] * W_256^(pk) ----
+  dft8(zr, zi);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k) cmul(zr[k], zi[k], t1r[k], t1i[k]);
+    const int idx = piA(8 * lane + k);
+    Er[idx] = zr[k]; Ei[idx] = zi[k];
+  }
+  __syncwarp();
+  // ---- pass 2: radix 8 (n=32, s=8): j = q + 8p reads E[j + 32r], writes E'[q + 64p + 8k] ----
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int idx = piA(lane + 32 * r);
+    zr[r] = Er[idx]; zi[r] = Ei[idx];
+  }
+  __syncwarp();                                   // same buffer, other layout: every lane has read before any writes
+  dft8(zr, zi);
+  {
+    const int q = lane & 7, p = lane >> 3;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (k) cmul(zr[k], zi[k], t1r[k], t1i[k]);
-      const int idx = piA(8 * lane + k);
-      Ar[idx] = zr[k]; Ai[idx] = zi[k];
+      if (k) cmul(zr[k], zi[k], t2r[k], t2i[k]);
+      const int idx = piB(q + 64 * p + 8 * k);
+      Er[idx] = zr[k]; Ei[idx] = zi[k];
     }
-    __syncwarp();
-    // ---- pass 2: radix 8 (n=32, s=8): j = q + 8p reads A[j + 32r], writes B[q + 64p + 8k] ----
+  }
+  __syncwarp();
+  // ---- pass 3: radix 4 (n=4, s=64): q = lane + 32 hh reads E'[q + 64r]; Z[q + 64k] stays in registers as element hh + 2k
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int idx = piA(lane + 32 * r);
-      zr[r] = Ar[idx]; zi[r] = Ai[idx];
-    }
-    dft8(zr, zi);
-    {
-      const int q = lane & 7, p = lane >> 3;
+  for (int hh = 0; hh < 2; ++hh) {
+    const int q = lane + 32 * hh;
+    const float r0 = Er[piB(q)], i0 = Ei[piB(q)];
+    const float r1 = Er[piB(q + 64)], i1 = Ei[piB(q + 64)];
+    const float r2 = Er[piB(q + 128)], i2 = Ei[piB(q + 128)];
+    const float r3 = Er[piB(q + 192)], i3 = Ei[piB(q + 192)];
+    const float s0r = r0 + r2, s0i = i0 + i2, d0r = r0 - r2, d0i = i0 - i2;
+    const float s1r = r1 + r3, s1i = i1 + i3, d1r = r1 - r3, d1i = i1 - i3;
+    zr[hh] = s0r + s1r;      zi[hh] = s0i + s1i;
+    zr[hh + 2] = d0r + d1i;  zi[hh + 2] = d0i - d1r;     // d0 - i d1
+    zr[hh + 4] = s0r - s1r;  zi[hh + 4] = s0i - s1i;
+    zr[hh + 6] = d0r - d1i;  zi[hh + 6] = d0i + d1r;     // d0 + i d1
+  }
+  __syncwarp();                                   // the exchange buffer is free again (pw may alias it)
+  // ---- real-FFT untangle + power spectrum -> pw[0..255] ----
+  float cr[8], ci[8];
+  {
+    const int src = (32 - lane) & 31;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (k) cmul(zr[k], zi[k], t2r[k], t2i[k]);
-        const int idx = piB(q + 64 * p + 8 * k);
-        Br[idx] = zr[k]; Bi[idx] = zi[k];
-      }
+    for (int j = 0; j < 8; ++j) {
+      cr[j] = __shfl_sync(0xffffffffu, zr[j], src);
+      ci[j] = __shfl_sync(0xffffffffu, zi[j], src);
     }
-    __syncwarp();
-    // ---- pass 3: radix 4 (n=4, s=64): q reads B[q + 64r], writes Z[q + 64k] into A ----
+  }
+  const bool l0 = lane == 0;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int q = lane + 32 * hh;
-      float r0 = Br[piB(q)], i0 = Bi[piB(q)];
-      float r1 = Br[piB(q + 64)], i1 = Bi[piB(q + 64)];
-      float r2 = Br[piB(q + 128)], i2 = Bi[piB(q + 128)];
-      float r3 = Br[piB(q + 192)], i3 = Bi[piB(q + 192)];
-      const float s0r = r0 + r2, s0i = i0 + i2, d0r = r0 - r2, d0i = i0 - i2;
-      const float s1r = r1 + r3, s1i = i1 + i3, d1r = r1 - r3, d1i = i1 - i3;
-      Ar[piA(q)] = s0r + s1r;        Ai[piA(q)] = s0i + s1i;
-      Ar[piA(q + 64)] = d0r + d1i;   Ai[piA(q + 64)] = d0i - d1r;     // d0 - i d1
-      Ar[piA(q + 128)] = s0r - s1r;  Ai[piA(q + 128)] = s0i - s1i;
-      Ar[piA(q + 192)] = d0r - d1i;  Ai[piA(q + 192)] = d0i + d1r;    // d0 + i d1
-    }
-    __syncwarp();
-    // ---- real-FFT untangle + power spectrum -> pw[0..255] ----
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = lane + 32 * i;
-      const int kn = (NBIN - k) & (NBIN - 1);
-      const float ar = Ar[piA(k)], ai = Ai[piA(k)];
-      const float cr = Ar[piA(kn)], ci = Ai[piA(kn)];
-      const float er = 0.5f * (ar + cr), ei = 0.5f * (ai - ci);
-      const float dr = 0.5f * (ar - cr), di = 0.5f * (ai + ci);
-      const float2 w = s_tw512[k];
-      const float p = w.x * dr - w.y * di, q = w.x * di + w.y * dr;
-      const float xr = er + q, xi = ei - p;
-      pw[k] = xr * xr + xi * xi;
-    }
-    __syncwarp();
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
+    const float ar = zr[i], ai = zi[i];
+    const float pr = l0 ? cr[(8 - i) & 7] : cr[7 - i], pi = l0 ? ci[(8 - i) & 7] : ci[7 - i];
+    const float er = 0.5f * (ar + pr), ei = 0.5f * (ai - pi);
+    const float dr = 0.5f * (ar - pr), di = 0.5f * (ai + pi);
+    const float2 w = s_tw512[k];
+    const float p = w.x * dr - w.y * di, q = w.x * di + w.y * dr;
+    const float xr = er + q, xi = ei - p;
+    pw[k] = xr * xr + xi * xi;
+  }
+  __syncwarp();
 }
 
 }  // namespace fbcore
