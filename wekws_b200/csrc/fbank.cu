@@ -38,7 +38,7 @@ using fbcore::WIN; using fbcore::SHIFT; using fbcore::NFFT; using fbcore::NBIN; 
 constexpr int STAGE = (FB_FRAMES - 1) * SHIFT + WIN;  // 5360 samples
 constexpr int MAX_MEL = 128;
 constexpr int P_ST = NBIN + 1;              // row pitch of the power-spectrum tile (odd: lane = frame reads are conflict-free)
-constexpr int O_ST = MAX_MEL + 1;           // row pitch of the output staging tile (aliases the PCM stage)
+constexpr int O_ST = MAX_MEL + 4;           // row pitch of the output staging tile (aliases the PCM stage; 16-byte rows)
 static_assert(FB_FRAMES == 32, "the mel phase maps one frame to one lane");
 static_assert(FB_FRAMES * O_ST <= STAGE, "output staging must fit in the PCM stage");
 static_assert(STAGE % 8 == 0, "vector staging");
@@ -57,6 +57,8 @@ struct FbankArgs {
   long long B, num_samples, pcm_stride, max_frames;
   int nmel;
   float preemph, log_floor;
+  float log_of_floor;       // logf(log_floor), evaluated on the host: flooring bins get exactly the reference's constant
+  int out_vec_ok;           // output rows are 16-byte aligned multiples of 4 floats: tile rows leave with 16-byte stores
   int remove_dc;
   int vec_ok;               // every stream starts 16-byte aligned: stage PCM with 16-byte loads
   // tables (device)
@@ -82,6 +84,24 @@ struct MelTable {
   float w[MW_MAX];                          // non-zero weights, row after row
   int16_t start[MAX_MEL], cnt[MAX_MEL], off[MAX_MEL];   // per mel bin: first fft bin, taps, offset into w
 };
+
+// Natural logarithm for the log-mel epilogue: MUFU lg2 gives log2(x) to ~2^-22 relative, one Newton step on
+// 2^-t x = 1 + delta removes that error (log x = ln2 t + log(1 + delta), |delta| < 1e-5 so log(1 + delta) = delta to
+// 1e-11): max error 1.3e-6 at |log x| ~ 16 against 1.1e-6 for libm's logf (float64 truth; profiles/r02_fbank_notes.md), in 6
+// instructions instead of 32.  x must be a positive normal float (callers floor at log_floor and route anything else
+// to logf).
+__device__ __forceinline__ float log_newton(float x) {
+  float t, e;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t));
+  return fmaf(0.693147180559945309f, t, fmaf(x, e, -1.0f));
+}
+// log(max(e, floor)) as kaldi.py:633 computes it
+__device__ __forceinline__ float log_floored(float e, float floor_v, float log_of_floor) {
+  const float x = fmaxf(e, floor_v);
+  if (!(x >= 1.17549435e-38f && x <= 1.0e37f)) return logf(x);        // denormal floor, 2^-t would underflow, inf, nan: never in practice
+  return x == floor_v ? log_of_floor : log_newton(x);
+}
 
 // MFCC = true adds the cepstral epilogue: the log-mel rows of the warp's FB_FPW frames stay in registers
 // (lane owns bins lane + 32 k) and are multiplied with the DCT matrix together, so every matrix element is
@@ -110,27 +130,60 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
 
   float* Br = s_bufB[warp][0]; float* Bi = s_bufB[warp][1];
 
-  const long long nfb = (a.max_frames + FB_FRAMES - 1) / FB_FRAMES;
-  const long long items = a.B * nfb;
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const long long b = item / nfb;
-    const long long f0 = (item - b * nfb) * FB_FRAMES;
-    long long len = a.lens ? (long long)a.lens[b] : a.num_samples;
-    if (len > a.num_samples) len = a.num_samples;
-    long long mb = len < WIN ? 0 : 1 + (len - WIN) / SHIFT;
-    if (mb > a.max_frames) mb = a.max_frames;
+  // Work items: (stream b, block of 32 frames fblk).  Per-stream quantities are 32-bit (the host checks the sizes);
+  // a CTA steps through its items by adding (gridDim / nfb, gridDim % nfb) -- no division in the loop.
+  const int max_frames = (int)a.max_frames, num_samples = (int)a.num_samples;
+  const int nfb = (max_frames + FB_FRAMES - 1) / FB_FRAMES;
+  const int items = (int)a.B * nfb;
+  const int db = (int)gridDim.x / nfb, dfb = (int)gridDim.x % nfb;
+  int b = (int)blockIdx.x / nfb, fblk = (int)blockIdx.x % nfb;
+  // int16 log-mel kernel: the 16-byte vectors of the NEXT work item are requested right after the FFT phase and sit in
+  // registers through the (register-light) mel and store phases, so the staging at the top of the loop converts data
+  // that has already arrived instead of waiting a DRAM round trip with the whole CTA at the barrier.
+  constexpr int VW = 16 / (int)sizeof(PCM);       // samples per 16-byte load
+  constexpr bool PRE = !MFCC && sizeof(PCM) == 2;
+  constexpr int NV = (STAGE / VW + FB_NT - 1) / FB_NT;
+  uint4 pre[PRE ? NV : 1];
+  auto item_len = [&](int bb) {
+    const int len = a.lens ? a.lens[bb] : num_samples;
+    return len > num_samples ? num_samples : len;
+  };
+  auto prefetch = [&](int bb, int fb) {
+    const int base = fb * FB_FRAMES * SHIFT, len = item_len(bb);
+    const PCM* src = reinterpret_cast<const PCM*>(a.pcm) + (long long)bb * a.pcm_stride;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = tid + k * FB_NT;
+      const int n = base + i * VW;
+      const bool full = i < STAGE / VW && n + VW <= len;     // partial / absent vectors take the scalar path at staging
+      pre[k] = full ? __ldg(reinterpret_cast<const uint4*>(src + n)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  const bool use_pre = PRE && a.vec_ok;
+  if (use_pre && (int)blockIdx.x < items) prefetch(b, fblk);
+  auto advance = [&]() {
+    fblk += dfb; b += db;
+    if (fblk >= nfb) { fblk -= nfb; ++b; }
+  };
+  for (int item = blockIdx.x; item < items; item += gridDim.x, advance()) {
+    const int f0 = fblk * FB_FRAMES;
+    const int len = item_len(b);
+    int mb = len < WIN ? 0 : 1 + (len - WIN) / SHIFT;
+    if (mb > max_frames) mb = max_frames;
 
     __syncthreads();
     {
-      const PCM* src = reinterpret_cast<const PCM*>(a.pcm) + b * a.pcm_stride;
-      const long long base = f0 * SHIFT;            // multiple of 160 samples: 16-byte aligned when the stream is
-      constexpr int VW = 16 / (int)sizeof(PCM);     // samples per 16-byte load
+      const PCM* src = reinterpret_cast<const PCM*>(a.pcm) + (long long)b * a.pcm_stride;
+      const int base = f0 * SHIFT;                  // multiple of 160 samples: 16-byte aligned when the stream is
       if (a.vec_ok) {
-        for (int i = tid; i < STAGE / VW; i += FB_NT) {
-          const long long n = base + (long long)i * VW;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int i = tid + k * FB_NT;
+          if (i >= STAGE / VW) break;
+          const int n = base + i * VW;
           float* d = s_stage + i * VW;
           if (n + VW <= len) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + n));
+            const uint4 v = PRE ? pre[PRE ? k : 0] : __ldg(reinterpret_cast<const uint4*>(src + n));
             if (sizeof(PCM) == 2) {
               const uint32_t w[4] = {v.x, v.y, v.z, v.w};
               float f[8];
@@ -152,7 +205,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
         }
       } else {
         for (int i = tid; i < STAGE; i += FB_NT) {
-          const long long n = base + i;
+          const int n = base + i;
           s_stage[i] = n < len ? (float)src[n] : 0.f;
         }
       }
@@ -169,6 +222,11 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
         }
       }
       __syncthreads();                              // spectra complete; the PCM stage is dead and becomes the output tile
+      if (use_pre && item + (int)gridDim.x < items) {
+        int nb = b + db, nf = fblk + dfb;
+        if (nf >= nfb) { nf -= nfb; ++nb; }
+        prefetch(nb, nf);
+      }
       // ---- mel projection (sparse rows, kaldi.py:630), log floor, CMVN: lane = frame, one mel bin per warp at a time.
       // Rows of absent frames hold stale values; they are never stored.
       float* s_o = s_stage;
@@ -180,7 +238,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
           float e = 0.f;
 #pragma unroll 4
           for (int i = 0; i < cnt; ++i) e = fmaf(mt.w[off + i], p[i], e);
-          float v = logf(fmaxf(e, a.log_floor));
+          float v = log_floored(e, a.log_floor, a.log_of_floor);
           if (a.mean) v -= __ldg(a.mean + m);
           if (a.istd) v *= __ldg(a.istd + m);
           s_o[lane * O_ST + m] = v;
@@ -189,11 +247,17 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
       __syncthreads();
       for (int fi = 0; fi < FB_FPW; ++fi) {
         const int fl = warp + FB_WARPS * fi;
-        const long long f = f0 + fl;
-        if (f >= a.max_frames) continue;
-        float* outp = a.out + (b * a.max_frames + f) * a.odim;
+        const int f = f0 + fl;
+        if (f >= max_frames) continue;
+        float* outp = a.out + ((long long)b * max_frames + f) * a.odim;
         const bool live = f < mb;
-        for (int m = lane; m < a.nmel; m += 32) outp[m] = live ? s_o[fl * O_ST + m] : 0.f;
+        if (a.out_vec_ok) {                         // nmel <= 128: one 16-byte load + store per lane
+          if (4 * lane < a.nmel)
+            reinterpret_cast<float4*>(outp)[lane] =
+                live ? *reinterpret_cast<const float4*>(s_o + fl * O_ST + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int m = lane; m < a.nmel; m += 32) outp[m] = live ? s_o[fl * O_ST + m] : 0.f;
+        }
       }
       continue;                                     // the barrier at the top of the loop protects s_o
     }
@@ -208,9 +272,9 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
     }
     for (int fi = 0; fi < FB_FPW; ++fi) {
     const int fl = warp + FB_WARPS * fi;          // frame of this warp within the item
-    const long long f = f0 + fl;
-    if (f >= a.max_frames) continue;          // warp-uniform; no block barrier inside this loop
-    float* outp = a.out + (b * a.max_frames + f) * a.odim;
+    const int f = f0 + fl;
+    if (f >= max_frames) continue;            // warp-uniform; no block barrier inside this loop
+    float* outp = a.out + ((long long)b * max_frames + f) * a.odim;
     if (f >= mb) {
       for (int m = lane; m < a.odim; m += 32) outp[m] = 0.f;
       continue;
@@ -229,7 +293,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
           const float* w = s_mw + __ldg(a.moff + m);
           float e = 0.f;
           for (int i = 0; i < cnt; ++i) e = fmaf(w[i], Br[st + i], e);
-          const float v = logf(fmaxf(e, a.log_floor));
+          const float v = log_floored(e, a.log_floor, a.log_of_floor);
 #pragma unroll
           for (int ff = 0; ff < FB_FPW; ++ff)
             if (fi == ff) lm[ff][k] = v;          // warp-uniform select keeps the row in registers
@@ -267,7 +331,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
 #pragma unroll
       for (int ff = 0; ff < FB_FPW; ++ff) {
         if (!((fvalid >> ff) & 1u)) continue;
-        float* orow = a.out + (b * a.max_frames + f0 + warp + FB_WARPS * ff) * a.odim;
+        float* orow = a.out + ((long long)b * max_frames + f0 + warp + FB_WARPS * ff) * a.odim;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c = lane + 32 * cc;
@@ -413,6 +477,8 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.pcm = d_pcm; a.lens = d_lens; a.mean = d_mean; a.istd = d_istd; a.out = d_out;
   a.B = B; a.num_samples = num_samples; a.pcm_stride = pcm_stride; a.max_frames = max_frames;
   a.nmel = fb->cfg.num_mel_bins; a.preemph = fb->cfg.preemphasis; a.log_floor = fb->cfg.log_floor;
+  a.log_of_floor = (float)log((double)fb->cfg.log_floor);
+  a.out_vec_ok = (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && fb->nceps == 0 && fb->cfg.num_mel_bins % 4 == 0;
   a.remove_dc = fb->cfg.remove_dc;
   a.tw256 = fb->d_tw256; a.tw512 = fb->d_tw512; a.window = fb->d_window;
   a.mstart = fb->d_mstart; a.mcnt = fb->d_mcnt; a.moff = fb->d_moff; a.mw = fb->d_mw;
@@ -420,6 +486,9 @@ extern "C" int wekws_fbank_forward(wekws_fbank* fb, const void* d_pcm, int pcm_d
   a.dct = fb->d_dct; a.lifter = fb->d_lifter; a.nceps = fb->nceps;
   a.odim = fb->nceps > 0 ? fb->nceps : fb->cfg.num_mel_bins;
   const long long items = B * ((max_frames + FB_FRAMES - 1) / FB_FRAMES);
+  WEKWS_REQUIRE(num_samples < (1ll << 31) - STAGE && max_frames < (1ll << 31) - FB_FRAMES && items < (1ll << 31) - 65536,
+                "wekws_fbank_forward: %lld samples x %lld streams is more than one call handles (split the batch)",
+                (long long)num_samples, (long long)B);
   const bool mf = fb->nceps > 0;
   const int esz = pcm_dtype == WEKWS_PCM_S16 ? 2 : 4;
   const size_t smem = (size_t)(SMEM_FLOATS_COMMON + (mf ? MW_MAX : FB_FRAMES * P_ST)) * sizeof(float);

@@ -82,7 +82,7 @@ __device__ __forceinline__ void frame_power_spectrum(const float* __restrict__ s
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = remove_dc ? sum / (float)WIN : 0.f;
+  const float mean = remove_dc ? sum * (1.0f / (float)WIN) : 0.f;   // (the reference's torch.mean sums in another order anyway)
   float zr[8], zi[8];
 #pragma unroll
   for (int i = 0; i < 7; ++i) {

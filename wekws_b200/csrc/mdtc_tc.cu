@@ -89,20 +89,6 @@ struct Bars {
   uint64_t *mma_bar, *halo_bar, *a_rdy, *h_free, *w_bar, *w_free, *vec_bar, *stg_bar;
 };
 
-// Streams of a pass -> tiles.  Sequential fill (3, 3, 1 for 7 streams of 40 frames) or, with `balanced`, an even split
-// over the same number of tiles (3, 2, 2): the groups then run closer to lock step and no loader serves three streams
-// while another serves one.
-struct TileSplit {
-  int ns, ntile, spt;
-  bool balanced;
-  __device__ __forceinline__ int count(int i) const {
-    return balanced ? ns / ntile + (i < ns % ntile ? 1 : 0) : min(spt, ns - i * spt);
-  }
-  __device__ __forceinline__ int first(int i) const {
-    return balanced ? i * (ns / ntile) + min(i, ns % ntile) : i * spt;
-  }
-};
-
 // WEIGHT / VECTOR RING (one thread): slot 0 carries Linear atom 0, W1(0), W1(1), ...; slot 1 [Linear atom 1], W2(0), ...
 __device__ __noinline__ void weights_role(const TcArgs& a, uint8_t* base, Bars B, int K, int natoms, uint32_t& wf_par,
                                           bool first_pass) {
@@ -137,8 +123,7 @@ __device__ __noinline__ void loader_role(const TcArgs& a, uint8_t* base, Bars B,
   float* STG = reinterpret_cast<float*>(base + OFF_STG);
   const uint32_t xs = smem_u32(base) + OFF_X;
   const int T = a.T, PADR = a.padr, Lw = a.padr + T, spt = a.spt;
-  const TileSplit ts{ns, ntile, spt, (a.debug & 2) != 0};
-  const int nst = ts.count(i), sg0 = ts.first(i);                 // my streams: sg0 .. sg0 + nst
+  const int nst = min(spt, ns - i * spt), sg0 = i * spt;          // my streams: sg0 .. sg0 + nst
   const int njobs = a.nblocks * nst;
   const bool have_cache = a.in_cache != nullptr;
   // landing slots of tile t: the streams' share of the NSLOT slots (each tile at least one; ns <= NSLOT: one per stream)
@@ -146,7 +131,7 @@ __device__ __noinline__ void loader_role(const TcArgs& a, uint8_t* base, Bars B,
   {
     int used = 0;
     for (int t = 0; t < ntile; ++t) {
-      const int n_t = ts.count(t);
+      const int n_t = min(spt, ns - t * spt);
       int want = ns <= NSLOT ? n_t : max(1, (NSLOT * n_t) / ns);
       const int left = NSLOT - used - (ntile - 1 - t);               // keep one slot for every later tile
       if (want > left) want = left;
@@ -301,7 +286,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
     const int b0 = done;
     done += ns;
     const int ntile = (ns + spt - 1) / spt;
-    const TileSplit ts{ns, ntile, spt, (a.debug & 2) != 0};
+    auto tile_streams = [&](int i) { return min(spt, ns - i * spt); };  // streams of tile i (sequential fill)
 
     // the landing slots are dealt out per pass (by stream count): their barriers start every pass from phase 0
     if (tid == 0) {
@@ -314,10 +299,10 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
       // warp = grp * WPG + 4 g + q: q = warp % 4 is the TMEM lane quarter the hardware lets this warp touch
       const int grp = warp / WPG, q = warp & 3, g = (warp % WPG) >> 2, wq = warp % WPG, row = 32 * q + lane;
       if (grp < ntile) {
-        const int nst = ts.count(grp), sg_first = ts.first(grp), rows = nst * T;
+        const int nst = tile_streams(grp), rows = nst * T;
         const bool live = row < rows, q_live = 32 * q < rows;
         const int s = live ? row / T : 0, tt = live ? row - s * T : 0;
-        const int sg = sg_first + s;                       // stream index inside the pass
+        const int sg = grp * spt + s;                      // stream index inside the pass
         const int col = sg * Lw + PADR + tt;               // this row's frame column (dead rows alias a valid one)
         const uint32_t t_own = xs + ((uint32_t)col << 8) + (((uint32_t)col & 7u) << 4);
         const uint32_t tm_row = tmem + ((uint32_t)(32 * q) << 16) + TM_TILE * grp;
@@ -524,7 +509,7 @@ __global__ void __launch_bounds__(NT_TC, 1) mdtc_tc_kernel(const __grid_constant
             const int nitem = nst * per;
             for (int it = wq; it < nitem; it += WPG) {
               const int s2 = it / per, cq = (it - s2 * per) * qstep + qs;
-              const int sg2 = sg_first + s2;
+              const int sg2 = grp * spt + s2;
               const uint32_t cc = (uint32_t)(sg2 * Lw + PADR + T - pad + j);
               const uint32_t src = ((xs + (cc << 8) + ((cc & 7u) << 4)) ^ ((uint32_t)(cq >> 1) << 4)) + (uint32_t)(cq & 1) * 128u;
               f32x2 v01, v23;
@@ -745,7 +730,7 @@ int mdtc_tc_launch(TcArgs a, int padmax, cudaStream_t st) {
   a.smax = smax;
   {
     const char* dbg = getenv("WEKWS_TC_DEBUG");     // bit 0: depthwise-phase token on (A/B timing; results unchanged)
-    a.debug = dbg ? atoi(dbg) : 0;                  // bit 1: balanced split of a pass's streams over its tiles
+    a.debug = dbg ? atoi(dbg) : 0;
   }
   // tensor maps over the incoming cache (B*64 rows of P floats): one per distinct slice width
   if (a.in_cache != nullptr) {
