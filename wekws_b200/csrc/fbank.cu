@@ -10,7 +10,7 @@
 // One warp owns one frame for the FFT.  The 512-point real FFT is a 256-point complex FFT of the
 // even/odd packed frame, done as a radix-8 / radix-8 / radix-4 Stockham autosort with the
 // first radix-8 entirely in registers (lane p holds z[p + 32 r]), two exchanges through one
-// bank-conflict-free padded per-warp shared buffer, and the real-FFT untangle by warp shuffles;
+// padded per-warp shared buffer of (re, im) pairs (8-byte accesses), and the real-FFT untangle by warp shuffles;
 // lane-constant twiddles live in registers.  A CTA (8 warps) stages the 5360 samples its 32
 // consecutive frames need once (16-byte loads, kept in the PCM type: int16 audio costs 10.5 KB),
 // so each PCM byte is read from HBM ~1.05x and each output byte written once.  The log-mel kernel
@@ -34,7 +34,7 @@ constexpr int FB_WARPS = 8;                 // warps per CTA
 constexpr int FB_FPW = 4;                   // frames per warp per work item
 constexpr int FB_FRAMES = FB_WARPS * FB_FPW; // frames per CTA work item (one staging load)
 constexpr int FB_NT = FB_WARPS * 32;
-using fbcore::WIN; using fbcore::SHIFT; using fbcore::NFFT; using fbcore::NBIN; using fbcore::B_SZ;
+using fbcore::WIN; using fbcore::SHIFT; using fbcore::NFFT; using fbcore::NBIN; using fbcore::E_SZ;
 constexpr int STAGE = (FB_FRAMES - 1) * SHIFT + WIN;  // 5360 samples
 constexpr int MAX_MEL = 128;
 constexpr int P_ST = NBIN + 1;              // row pitch of the power-spectrum tile (odd: lane = frame reads are conflict-free)
@@ -45,7 +45,7 @@ static_assert(STAGE % 8 == 0, "vector staging");
 // shared-memory layout (floats): [PCM stage as float / output tile][exchange buffers][tw512][window]
 // [log-mel kernel: power tile | MFCC kernel: mel weights]
 constexpr int MW_MAX = 2 * NBIN + 64;       // non-zero mel weights supported (80 bins at 16 kHz: 501)
-constexpr int SMEM_FLOATS_COMMON = STAGE + FB_WARPS * 2 * B_SZ + 2 * NBIN + WIN;
+constexpr int SMEM_FLOATS_COMMON = STAGE + FB_WARPS * 2 * E_SZ + 2 * NBIN + WIN;
 static_assert((SMEM_FLOATS_COMMON + FB_FRAMES * P_ST) * 4 + 1024 <= 233472 / 3, "the log-mel kernel must fit three times per SM");
 
 struct FbankArgs {
@@ -110,8 +110,8 @@ template <typename PCM, bool MFCC>
 __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankArgs a, const __grid_constant__ MelTable mt) {
   extern __shared__ __align__(16) float fb_smem[];
   float* s_stage = fb_smem;                                              // [STAGE]
-  float (*s_bufB)[2][B_SZ] = reinterpret_cast<float (*)[2][B_SZ]>(s_stage + STAGE);
-  float2* s_tw512 = reinterpret_cast<float2*>(s_stage + STAGE + FB_WARPS * 2 * B_SZ);
+  float2* s_ex = reinterpret_cast<float2*>(s_stage + STAGE);              // [FB_WARPS][E_SZ] exchange buffers
+  float2* s_tw512 = s_ex + FB_WARPS * E_SZ;                              // 0.5 W_512^k
   float2* s_win = s_tw512 + NBIN;
   float* s_pow = reinterpret_cast<float*>(s_win + WIN / 2);              // [FB_FRAMES][P_ST] (log-mel kernel)
   float* s_mw = s_pow;                                                   // [MW_MAX] (MFCC kernel: per-lane mel rows)
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
   // warp-uniform for the compiler too: the per-frame branches below are then uniform and the shuffles inside them
   // need no WARPSYNC / collective bracket
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  for (int i = tid; i < NBIN; i += FB_NT) s_tw512[i] = a.tw512[i];
+  for (int i = tid; i < NBIN; i += FB_NT) s_tw512[i] = make_float2(0.5f * a.tw512[i].x, 0.5f * a.tw512[i].y);
   for (int i = tid; i < WIN / 2; i += FB_NT) s_win[i] = make_float2(a.window[2 * i], a.window[2 * i + 1]);
   if (MFCC)
     for (int i = tid; i < a.mw_total; i += FB_NT) s_mw[i] = a.mw[i];
@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
   fbcore::LaneTwiddles tw;
   tw.load(a.tw256, lane);
 
-  float* Br = s_bufB[warp][0]; float* Bi = s_bufB[warp][1];
+  float2* E = s_ex + warp * E_SZ;
+  float* Br = reinterpret_cast<float*>(E);      // MFCC kernel: the frame's power spectrum lands in the (free) exchange buffer
 
   // Work items: (stream b, block of 32 frames fblk).  Per-stream quantities are 32-bit (the host checks the sizes);
   // a CTA steps through its items by adding (gridDim / nfb, gridDim % nfb) -- no division in the loop.
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
       for (int fi = 0; fi < FB_FPW; ++fi) {
         const int fl = warp + FB_WARPS * fi;
         if (f0 + fl < mb) {
-          fbcore::frame_power_spectrum(s_stage + fl * SHIFT, s_win, s_tw512, tw, Br, Bi, s_pow + fl * P_ST, a.preemph,
+          fbcore::frame_power_spectrum(s_stage + fl * SHIFT, s_win, s_tw512, tw, E, s_pow + fl * P_ST, a.preemph,
                                        a.remove_dc, lane);
         }
       }
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
       continue;
     }
 
-    fbcore::frame_power_spectrum(s_stage + fl * SHIFT, s_win, s_tw512, tw, Br, Bi, Br, a.preemph, a.remove_dc, lane);
+    fbcore::frame_power_spectrum(s_stage + fl * SHIFT, s_win, s_tw512, tw, E, Br, a.preemph, a.remove_dc, lane);
     __syncwarp();
     // ---- mel projection (sparse rows), log floor ----
     {

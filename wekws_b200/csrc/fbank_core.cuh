@@ -10,10 +10,11 @@ namespace wekws {
 namespace fbcore {
 
 constexpr int WIN = 400, SHIFT = 160, NFFT = 512, NBIN = 256;
-constexpr int B_SZ = 280;                   // padded exchange buffer (floats): holds the piA (264) and the piB (280) layout
+constexpr int E_SZ = 288;                   // padded exchange buffer of a warp (complex elements)
 
-__device__ __forceinline__ int piA(int i) { return i + (i >> 5); }
-__device__ __forceinline__ int piB(int i) { return i + 8 * (i >> 6); }
+// Element i of an exchange sits at i + i / 8: with 8-byte (re, im) elements a half-warp then touches 16 different
+// 8-byte bank pairs in the two write patterns (9 lane + k; q + 72 p + 9 k) and 15 of 16 in the two read patterns.
+__device__ __forceinline__ int pe(int i) { return i + (i >> 3); }
 
 __device__ __forceinline__ void cmul(float& re, float& im, float wr, float wi) {
   const float t = re * wr - im * wi;
@@ -56,14 +57,16 @@ struct LaneTwiddles {
   }
 };
 
-// Power spectrum of one frame -> pw[0..255].  s: the frame's 400 samples as float (int16 scale).  Er/Ei: B_SZ floats each, private to the warp (both exchanges go through
-// them; pw may be Er).  s_win: window as (even, odd) pairs; s_tw512: W_512^k, k < 256.  All 32 lanes participate.
-// After the last radix-4 pass lane l holds Z[l + 32 i], i < 8, in registers; the real-FFT untangle needs Z[256 - k]
+// Power spectrum of one frame -> pw[0..255].  s: the frame's 400 samples as float (int16 scale).  E: E_SZ complex
+// elements private to the warp (both exchanges go through it as 8-byte loads / stores; pw may alias it).  s_win: window
+// as (even, odd) pairs; s_tw512h: 0.5 W_512^k, k < 256 (the 1/2 of the real-FFT untangle folded into the table: an exact
+// scaling, so the result is bit-identical to 0.5 (a +- b) followed by the rotation).  All 32 lanes participate.
+// After the last radix-4 pass lane l holds Z[l + 32 i], i < 8, in registers; the untangle needs Z[256 - k]
 // next to Z[k], which is element 7 - i of lane 32 - l (lane 0: its own element (8 - i) & 7) -- 16 shuffles instead
 // of a third trip through shared memory.
 __device__ __forceinline__ void frame_power_spectrum(const float* __restrict__ s, const float2* __restrict__ s_win,
-                                                     const float2* __restrict__ s_tw512, const LaneTwiddles& tw, float* Er,
-                                                     float* Ei, float* pw, float preemph, int remove_dc, int lane) {
+                                                     const float2* __restrict__ s_tw512h, const LaneTwiddles& tw, float2* E,
+                                                     float* pw, float preemph, int remove_dc, int lane) {
   const float* t1r = tw.t1r; const float* t1i = tw.t1i; const float* t2r = tw.t2r; const float* t2i = tw.t2i;
   // ---- window: lane owns packed points m = lane + 32 i (even/odd sample pair 2m, 2m+1) ----
   float xa[7], xb[7], xc[7];
@@ -103,38 +106,36 @@ __device__ __forceinline__ void frame_power_spectrum(const float* __restrict__ s
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (k) cmul(zr[k], zi[k], t1r[k], t1i[k]);
-    const int idx = piA(8 * lane + k);
-    Er[idx] = zr[k]; Ei[idx] = zi[k];
+    E[9 * lane + k] = make_float2(zr[k], zi[k]);      // pe(8 lane + k)
   }
   __syncwarp();
   // ---- pass 2: radix 8 (n=32, s=8): j = q + 8p reads E[j + 32r], writes E'[q + 64p + 8k] ----
+  {
+    const int b = lane + (lane >> 3);                 // pe(lane + 32 r) = b + 36 r
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int idx = piA(lane + 32 * r);
-    zr[r] = Er[idx]; zi[r] = Ei[idx];
+    for (int r = 0; r < 8; ++r) {
+      const float2 v = E[b + 36 * r];
+      zr[r] = v.x; zi[r] = v.y;
+    }
   }
   __syncwarp();                                   // same buffer, other layout: every lane has read before any writes
   dft8(zr, zi);
   {
-    const int q = lane & 7, p = lane >> 3;
+    const int b = (lane & 7) + 72 * (lane >> 3);      // pe(q + 64 p + 8 k) = q + 72 p + 9 k
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (k) cmul(zr[k], zi[k], t2r[k], t2i[k]);
-      const int idx = piB(q + 64 * p + 8 * k);
-      Er[idx] = zr[k]; Ei[idx] = zi[k];
+      E[b + 9 * k] = make_float2(zr[k], zi[k]);
     }
   }
   __syncwarp();
   // ---- pass 3: radix 4 (n=4, s=64): q = lane + 32 hh reads E'[q + 64r]; Z[q + 64k] stays in registers as element hh + 2k
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
-    const int q = lane + 32 * hh;
-    const float r0 = Er[piB(q)], i0 = Ei[piB(q)];
-    const float r1 = Er[piB(q + 64)], i1 = Ei[piB(q + 64)];
-    const float r2 = Er[piB(q + 128)], i2 = Ei[piB(q + 128)];
-    const float r3 = Er[piB(q + 192)], i3 = Ei[piB(q + 192)];
-    const float s0r = r0 + r2, s0i = i0 + i2, d0r = r0 - r2, d0i = i0 - i2;
-    const float s1r = r1 + r3, s1i = i1 + i3, d1r = r1 - r3, d1i = i1 - i3;
+    const int q = lane + 32 * hh, b = q + (q >> 3);   // pe(q + 64 r) = b + 72 r
+    const float2 v0 = E[b], v1 = E[b + 72], v2 = E[b + 144], v3 = E[b + 216];
+    const float s0r = v0.x + v2.x, s0i = v0.y + v2.y, d0r = v0.x - v2.x, d0i = v0.y - v2.y;
+    const float s1r = v1.x + v3.x, s1i = v1.y + v3.y, d1r = v1.x - v3.x, d1i = v1.y - v3.y;
     zr[hh] = s0r + s1r;      zi[hh] = s0i + s1i;
     zr[hh + 2] = d0r + d1i;  zi[hh + 2] = d0i - d1r;     // d0 - i d1
     zr[hh + 4] = s0r - s1r;  zi[hh + 4] = s0i - s1i;
@@ -157,11 +158,10 @@ __device__ __forceinline__ void frame_power_spectrum(const float* __restrict__ s
     const int k = lane + 32 * i;
     const float ar = zr[i], ai = zi[i];
     const float pr = l0 ? cr[(8 - i) & 7] : cr[7 - i], pi = l0 ? ci[(8 - i) & 7] : ci[7 - i];
-    const float er = 0.5f * (ar + pr), ei = 0.5f * (ai - pi);
-    const float dr = 0.5f * (ar - pr), di = 0.5f * (ai + pi);
-    const float2 w = s_tw512[k];
+    const float sr = ar + pr, si = ai - pi, dr = ar - pr, di = ai + pi;
+    const float2 w = s_tw512h[k];
     const float p = w.x * dr - w.y * di, q = w.x * di + w.y * dr;
-    const float xr = er + q, xi = ei - p;
+    const float xr = fmaf(0.5f, sr, q), xi = fmaf(0.5f, si, -p);
     pw[k] = xr * xr + xi * xi;
   }
   __syncwarp();
