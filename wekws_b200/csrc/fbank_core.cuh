@@ -10,11 +10,12 @@ namespace wekws {
 namespace fbcore {
 
 constexpr int WIN = 400, SHIFT = 160, NFFT = 512, NBIN = 256;
-constexpr int E_SZ = 288;                   // padded exchange buffer of a warp (complex elements)
+constexpr int E_SZ = 280;                   // padded exchange buffer of a warp (complex elements)
 
-// Element i of an exchange sits at i + i / 8: with 8-byte (re, im) elements a half-warp then touches 16 different
-// 8-byte bank pairs in the two write patterns (9 lane + k; q + 72 p + 9 k) and 15 of 16 in the two read patterns.
-__device__ __forceinline__ int pe(int i) { return i + (i >> 3); }
+// 8-byte (re, im) elements: a half-warp is served in one pass when its 16 elements fall into 16 different 8-byte bank
+// pairs (element index mod 16).  First exchange: element i at i + i / 16 (write 8 lane + k -> 8 lane + lane / 2 + k,
+// read lane + 32 r -> lane + lane / 16 + 34 r); second exchange: element i at i + 8 (i / 64) (write q + 64 p + 8 k ->
+// q + 72 p + 8 k, read q' + 64 r -> q' + 72 r).  All four patterns are conflict-free (checked exhaustively).
 
 __device__ __forceinline__ void cmul(float& re, float& im, float wr, float wi) {
   const float t = re * wr - im * wi;
@@ -106,34 +107,34 @@ __device__ __forceinline__ void frame_power_spectrum(const float* __restrict__ s
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (k) cmul(zr[k], zi[k], t1r[k], t1i[k]);
-    E[9 * lane + k] = make_float2(zr[k], zi[k]);      // pe(8 lane + k)
+    E[8 * lane + (lane >> 1) + k] = make_float2(zr[k], zi[k]);
   }
   __syncwarp();
   // ---- pass 2: radix 8 (n=32, s=8): j = q + 8p reads E[j + 32r], writes E'[q + 64p + 8k] ----
   {
-    const int b = lane + (lane >> 3);                 // pe(lane + 32 r) = b + 36 r
+    const int b = lane + (lane >> 4);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const float2 v = E[b + 36 * r];
+      const float2 v = E[b + 34 * r];
       zr[r] = v.x; zi[r] = v.y;
     }
   }
   __syncwarp();                                   // same buffer, other layout: every lane has read before any writes
   dft8(zr, zi);
   {
-    const int b = (lane & 7) + 72 * (lane >> 3);      // pe(q + 64 p + 8 k) = q + 72 p + 9 k
+    const int b = (lane & 7) + 72 * (lane >> 3);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (k) cmul(zr[k], zi[k], t2r[k], t2i[k]);
-      E[b + 9 * k] = make_float2(zr[k], zi[k]);
+      E[b + 8 * k] = make_float2(zr[k], zi[k]);
     }
   }
   __syncwarp();
   // ---- pass 3: radix 4 (n=4, s=64): q = lane + 32 hh reads E'[q + 64r]; Z[q + 64k] stays in registers as element hh + 2k
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
-    const int q = lane + 32 * hh, b = q + (q >> 3);   // pe(q + 64 r) = b + 72 r
-    const float2 v0 = E[b], v1 = E[b + 72], v2 = E[b + 144], v3 = E[b + 216];
+    const int q = lane + 32 * hh;
+    const float2 v0 = E[q], v1 = E[q + 72], v2 = E[q + 144], v3 = E[q + 216];
     const float s0r = v0.x + v2.x, s0i = v0.y + v2.y, d0r = v0.x - v2.x, d0i = v0.y - v2.y;
     const float s1r = v1.x + v3.x, s1i = v1.y + v3.y, d1r = v1.x - v3.x, d1i = v1.y - v3.y;
     zr[hh] = s0r + s1r;      zi[hh] = s0i + s1i;
