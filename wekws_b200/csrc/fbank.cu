@@ -80,9 +80,13 @@ struct FbankArgs {
 // warp works on ONE mel bin at a time (lane = frame), so the row's start / length / weights are warp-uniform and come
 // through the uniform datapath (LDCU) instead of competing with the per-lane spectrum loads for the shared-memory
 // pipe -- and the 3.8 KB of tables they used to occupy there is what lets a third CTA fit on the SM.
+// Rows are padded with zero weights to a multiple of 4 taps (a row that would run past bin 255 is shifted left
+// instead, with leading zeros), so the mel loop is 4 taps per trip with one 16-byte constant load and no remainder;
+// a zero weight adds exactly nothing (the spectra are finite and stay inside the frame's own row).
+constexpr int MW_PAD_MAX = MW_MAX + 3 * MAX_MEL;
 struct MelTable {
-  float w[MW_MAX];                          // non-zero weights, row after row
-  int16_t start[MAX_MEL], cnt[MAX_MEL], off[MAX_MEL];   // per mel bin: first fft bin, taps, offset into w
+  alignas(16) float w[MW_PAD_MAX];          // padded weights, row after row (every row starts 16-byte aligned)
+  int16_t start[MAX_MEL], cnt[MAX_MEL], off[MAX_MEL];   // per mel bin: first fft bin, padded taps, offset into w
 };
 
 // Natural logarithm for the log-mel epilogue: MUFU lg2 gives log2(x) to ~2^-22 relative, one Newton step on
@@ -234,11 +238,17 @@ __global__ void __launch_bounds__(FB_NT, MFCC ? 2 : 3) fbank_kernel(const FbankA
       {
         const float* prow = s_pow + lane * P_ST;
         for (int m = warp; m < a.nmel; m += FB_WARPS) {
-          const int st = mt.start[m], cnt = mt.cnt[m], off = mt.off[m];      // warp-uniform: constant bank
+          const int st = mt.start[m], cnt4 = mt.cnt[m], off = mt.off[m];     // warp-uniform: constant bank
           const float* p = prow + st;
           float e = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < cnt; ++i) e = fmaf(mt.w[off + i], p[i], e);
+#pragma unroll 1
+          for (int i = 0; i < cnt4; i += 4) {      // rows are 2 trips on average: no unrolling, no remainder code
+            const float4 w = *reinterpret_cast<const float4*>(&mt.w[off + i]);
+            e = fmaf(w.x, p[i], e);
+            e = fmaf(w.y, p[i + 1], e);
+            e = fmaf(w.z, p[i + 2], e);
+            e = fmaf(w.w, p[i + 3], e);
+          }
           float v = log_floored(e, a.log_floor, a.log_of_floor);
           if (a.mean) v -= __ldg(a.mean + m);
           if (a.istd) v *= __ldg(a.istd + m);
@@ -407,9 +417,21 @@ extern "C" int wekws_fbank_create(const wekws_fbank_config* cfg, const float* h_
   fb->cfg = *cfg;
   fb->mw_total = (int)mw.size();
   memset(&fb->mt, 0, sizeof(fb->mt));
-  for (size_t i = 0; i < mw.size(); ++i) fb->mt.w[i] = mw[i];
-  for (int m = 0; m < nm; ++m) {
-    fb->mt.start[m] = (int16_t)mstart[m]; fb->mt.cnt[m] = (int16_t)mcnt[m]; fb->mt.off[m] = (int16_t)moff[m];
+  {
+    int used = 0;                                   // padded rows (MelTable): zeros in front if the row is shifted left
+    for (int m = 0; m < nm; ++m) {
+      const int cnt4 = (mcnt[m] + 3) & ~3;
+      int st = mstart[m];
+      if (st + cnt4 > NBIN) st = NBIN - cnt4;
+      if (st < 0 || used + cnt4 > MW_PAD_MAX) {
+        delete fb;
+        set_error("fbank: mel filterbank does not fit the padded table");
+        return WEKWS_ERR_INVALID;
+      }
+      for (int k = 0; k < mcnt[m]; ++k) fb->mt.w[used + (mstart[m] - st) + k] = mw[moff[m] + k];
+      fb->mt.start[m] = (int16_t)st; fb->mt.cnt[m] = (int16_t)cnt4; fb->mt.off[m] = (int16_t)used;
+      used += cnt4;
+    }
   }
   WEKWS_CUDA_OK(cudaGetDevice(&fb->device));
 #define UP(dst, vec)                                                                      \
