@@ -12,13 +12,13 @@
 // first radix-8 entirely in registers (lane p holds z[p + 32 r]), two exchanges through one
 // padded per-warp shared buffer of (re, im) pairs (8-byte accesses), and the real-FFT untangle by warp shuffles;
 // lane-constant twiddles live in registers.  A CTA (8 warps) stages the 5360 samples its 32
-// consecutive frames need once (16-byte loads, kept in the PCM type: int16 audio costs 10.5 KB),
+// consecutive frames need once (16-byte loads, converted to float; the next item's vectors are prefetched),
 // so each PCM byte is read from HBM ~1.05x and each output byte written once.  The log-mel kernel
-// is sized for THREE CTAs per SM (73 KB of shared memory, <= 80 registers): 24 warps hide the
-// shared-memory and shuffle latencies of the FFT better than the 16 of the round-2 kernel.
+// is sized for THREE CTAs per SM (75.9 KB of shared memory, <= 80 registers): 24 warps hide the
+// shared-memory and shuffle latencies of the FFT better than the 16 of the mid-round-2 kernel.
 // The mel projection runs after all 32 power spectra of the work item are in shared memory, with
-// lane = frame and the (warp-uniform) sparse row of one mel bin per warp: no divergence between
-// lanes whatever the filter widths, 3 instructions per tap per 32 frames.
+// lane = frame and the (warp-uniform) sparse row of one mel bin per warp, read from the constant bank:
+// no divergence between lanes whatever the filter widths.
 #include <math.h>
 #include <string.h>
 #include <vector>
